@@ -1,0 +1,98 @@
+/* zigp.h -- C ABI of libzigp (B200 / sm_100a).
+ *
+ * The one accelerated path: the OnOffSVGP (zero-inflated sparse variational GP) ELBO, its gradient, and the
+ * predictive moments, i.e. what the reference evaluates in
+ *     OnOffSVGP.build_likelihood   onoffgpf/OnOffSVGP.py:107-122   (+ tf.gradients of it)
+ *     OnOffSVGP.build_prior_KL     onoffgpf/OnOffSVGP.py:73-105
+ *     OnOffSVGP.build_predict      onoffgpf/OnOffSVGP.py:124-152   (predict_onoffgp, :160-162)
+ * The reference has no FFI of its own (it is pure Python on GPflow 0.4 / TF1); these entry points are what a
+ * Python binding of that class calls instead of building the TF graph.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all floating point data is IEEE double, row-major, contiguous;
+ *   - "dev" pointers are device pointers on the context's GPU and are BORROWED (never freed, never retained past
+ *     the call unless stated); "host" pointers are ordinary host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); device-pointer calls are
+ *     asynchronous and stream-ordered, host-pointer calls return after the result is in host memory;
+ *   - every function returns 0 on success, a negative ZIGP_E* code otherwise; zigp_last_error() gives the text;
+ *   - a context is bound to one GPU and is not thread-safe (one context per GPU / rank);
+ *   - there is no CPU fallback: without a CUDA device zigp_create fails with ZIGP_ECUDA.
+ *
+ * Packed parameter vector `theta` (constrained values, length zigp_theta_len()):
+ *     ell_f[D], var_f, ell_g[D], var_g, noise_var, Zf[Mf*D], Zg[Mg*D], u_fm[Mf], u_gm[Mg], u_fs_sqrt[Mf], u_gs_sqrt[Mg]
+ *   (kernf.lengthscales, kernf.variance, kerng.lengthscales, kerng.variance, likelihood.variance, Zf, Zg, u_fm, u_gm,
+ *    u_fs_sqrt, u_gs_sqrt of onoffgpf/OnOffSVGP.py:26-71; q_sqrt is diagonal as in the reference, :34).
+ * Packed result `out` (length ZIGP_OUT_HEADER + theta_len):
+ *     out[0] = ELBO, out[1] = sum_n var_exp_n over the (global) batch, out[2] = KL,
+ *     out[3] = info (0 = ok, k > 0: Cholesky of Kmm failed at pivot ((k-1) % 2^20) of latent (k-1) / 2^20: 0 = f, 1 = g),
+ *     out[4 + i] = d ELBO / d theta[i]   (gradients w.r.t. the constrained values; the host applies the
+ *                                         softplus chain rule of gpflow.transforms.positive).
+ */
+#ifndef ZIGP_H
+#define ZIGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZIGP_OUT_HEADER 4
+#define ZIGP_MAX_D 8
+
+#define ZIGP_OK 0
+#define ZIGP_EINVAL (-1)   /* bad argument */
+#define ZIGP_ECUDA (-2)    /* CUDA runtime error (text in zigp_last_error) */
+#define ZIGP_ESTATE (-3)   /* call sequence error (e.g. no data set) */
+#define ZIGP_ENOTPD (-4)   /* Kmm + jitter*I not positive definite (host-pointer calls only) */
+
+typedef struct zigp_ctx zigp_ctx;
+
+/* Create a context on GPU `device` for Mf / Mg inducing points and D input dimensions (D <= ZIGP_MAX_D).
+ * jitter: added to diag(Kmm) (gpflow settings.numerics.jitter_level = 1e-6 at onoffgpf/OnOffSVGP.py:96-97).
+ * chunk_rows: points processed per pass of the N-stage pipeline (0 = default). */
+int zigp_create(zigp_ctx** ctx, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows);
+int zigp_destroy(zigp_ctx* ctx);
+const char* zigp_last_error(const zigp_ctx* ctx);   /* ctx may be NULL: error of the last failed zigp_create */
+int64_t zigp_theta_len(const zigp_ctx* ctx);
+
+/* Attach this rank's shard of the minibatch: X (n_local x D), Y (n_local).  scale = num_data / global batch size
+ * (onoffgpf/OnOffSVGP.py:119-120).  Device pointers are borrowed until the next set_data / destroy. */
+int zigp_set_data_dev(zigp_ctx* ctx, const double* X_dev, const double* Y_dev, int64_t n_local, double scale);
+/* Same from host memory: copies into context-owned device buffers on `stream` (pinned host memory makes it async). */
+int zigp_set_data_host(zigp_ctx* ctx, const double* X_host, const double* Y_host, int64_t n_local, double scale, void* stream);
+
+/* ELBO + gradient on one GPU (= accumulate + finish below).  build_likelihood + tf.gradients. */
+int zigp_elbo_grad_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
+int zigp_elbo_grad_host(zigp_ctx* ctx, const double* theta_host, double* out_host, void* stream);
+
+/* Data-parallel form.  accumulate: M-stage forward + the pass over this rank's points; leaves the per-shard partial
+ * sums (data term, noise gradient, and per latent the whitened statistics E (MxM), a (M) and the Kmn-side kernel
+ * gradient sums) in one packed device buffer.  The caller sums that buffer over ranks (one allreduce), then calls
+ * finish on every rank: O(M^3) backward, adds -KL and its gradient exactly once, writes `out`. */
+int zigp_accumulate_dev(zigp_ctx* ctx, const double* theta_dev, void* stream);
+int zigp_accum_buffer(zigp_ctx* ctx, double** buf_dev, int64_t* len);
+int zigp_finish_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
+
+/* KL(q(u_f)||p(u_f)) + KL(q(u_g)||p(u_g)) only (build_prior_KL / compute_prior_KL, onoffgpf/OnOffSVGP.py:73-105,164-166).
+ * out_dev[0] = KL, out_dev[1] = info. */
+int zigp_prior_kl_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
+
+/* build_predict (onoffgpf/OnOffSVGP.py:124-152): out9 is 9 x n_new, rows in the order of :152
+ * (gfmean, gfvar, gfmeanu, fmean, fvar, gmean, gvar, ephi_g, evar_phi_g). */
+int zigp_predict_dev(zigp_ctx* ctx, const double* theta_dev, const double* Xnew_dev, int64_t n_new, double* out9_dev, void* stream);
+int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xnew_host, int64_t n_new, double* out9_host, void* stream);
+
+/* Test / profiling hooks: view of an internal device buffer after the last call.
+ * name: "L","T","Kmm","alpha_w","beta","E","a","G","K","A","RA","V","Y","mean","var","gm","gv" ; latent 0 = f, 1 = g. */
+int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t zigp_launch_count(const zigp_ctx* ctx);
+/* algorithmic flop count of one ELBO+grad evaluation of the current data shard (12 M^2 per point per SURVEY 8(d)) and
+ * the flops the kernels actually execute (block-triangular tiles, 10 M^2 formulation) */
+int zigp_flop_counts(const zigp_ctx* ctx, double* algorithmic, double* executed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

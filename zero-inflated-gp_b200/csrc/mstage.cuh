@@ -1,0 +1,242 @@
+// M-stage kernels (everything that is O(M^2) / O(M^3) and independent of the data points):
+// Kmm construction, blocked Cholesky (diagonal 64x64 blocks factorised + inverted in shared memory, panels and trailing
+// updates through the DMMA engine), triangular inverse T = L^-1, KL, and the closed-form backward
+//     G_K = T^T Hs T,  Hs = E - EP - (EP)^T - (a aw^T + aw a^T)/2 + aw aw^T/2 + P/2 - I/2,  P = R^T R
+// (replaces the reference's autodiff through tf.cholesky / matrix_triangular_solve,
+//  onofftf/main.py:187-305).
+#pragma once
+#include "gemm_f64.cuh"
+#include "../../include/zigp.h"
+
+namespace zigp {
+
+constexpr int NB = 64;   // Cholesky block size (== M-stage engine tile)
+
+// Kmm[i,j] = var * exp(-0.5 * sum_d ((z_id - z_jd)/ell_d)^2) + jitter*[i==j]   (onofftf/main.py:53-57 with X2=None; the
+// squared distance is formed from differences, not the reference's expanded form -- DESIGN.md section 7).
+// Padding (i or j >= M): identity.
+__global__ void kmm_build_kernel(const double* __restrict__ Z, const double* __restrict__ ell, const double* __restrict__ var,
+                                 int M, int D, int Mp, double jitter, double* __restrict__ K) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Mp) return;
+    double v;
+    if (i < M && j < M) {
+        double r2 = 0.0;
+        for (int d = 0; d < D; d++) {
+            double t = (Z[i * D + d] - Z[j * D + d]) / ell[d];
+            r2 = fma(t, t, r2);
+        }
+        v = var[0] * exp(-0.5 * r2) + (i == j ? jitter : 0.0);
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    K[(long long)i * Mp + j] = v;
+}
+
+constexpr size_t POTRF_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+
+// Factorise one NB x NB diagonal block in shared memory (right-looking), invert the factor, write back
+// L (upper part zeroed), Dinv = L^-1 and Dinvt = L^-T (both NB x NB, ld NB).
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, long long lda, double* __restrict__ Dinv,
+                                                         double* __restrict__ Dinvt, int* __restrict__ info, int pivot_base, int latent) {
+    extern __shared__ __align__(16) double potrf_sm[];
+    double (*L)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_sm);
+    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_sm + NB * (NB + 1));
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 256) {
+        int i = e / NB, j = e % NB;
+        L[i][j] = (j <= i) ? A[(long long)i * lda + j] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < NB; j++) {
+        if (tid == 0) {
+            double d = L[j][j];
+            if (!(d > 0.0)) {
+                if (atomicCAS(info, 0, (latent << 20) + pivot_base + j + 1) == 0) {}
+            }
+            L[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double dj = L[j][j];
+        if (tid > j && tid < NB) L[tid][j] /= dj;
+        __syncthreads();
+        // trailing update of the lower triangle: rows i > j, columns j < k <= i
+        const int rem = NB - 1 - j;
+        for (int e = tid; e < rem * rem; e += 256) {
+            int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            if (k <= i) L[i][k] = fma(-L[i][j], L[k][j], L[i][k]);
+        }
+        __syncthreads();
+    }
+    // X = L^-1, column c by thread c (forward substitution)
+    for (int e = tid; e < NB * NB; e += 256) X[e / NB][e % NB] = 0.0;
+    __syncthreads();
+    if (tid < NB) {
+        const int c = tid;
+        X[c][c] = 1.0 / L[c][c];
+        for (int i = c + 1; i < NB; i++) {
+            double s = 0.0;
+            for (int k = c; k < i; k++) s = fma(L[i][k], X[k][c], s);
+            X[i][c] = -s / L[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+        int i = e / NB, j = e % NB;
+        A[(long long)i * lda + j] = L[i][j];
+        Dinv[i * NB + j] = X[i][j];
+        Dinvt[i * NB + j] = X[j][i];
+    }
+}
+
+// zero the strict upper triangle (left dirty by the square trailing updates)
+__global__ void zero_upper_kernel(double* __restrict__ A, int Mp) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j < Mp && j > i) A[(long long)i * Mp + j] = 0.0;
+}
+
+// Out = In^T for square Mp x Mp (optionally scaling In's columns: Out[k,i] = In[i,k] * colscale[k])
+__global__ void transpose_kernel(const double* __restrict__ In, double* __restrict__ Out, int Mp, const double* __restrict__ colscale) {
+    __shared__ double t[32][33];
+    int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        double v = In[(long long)(by + r) * Mp + bx + threadIdx.x];
+        if (colscale) v *= colscale[bx + threadIdx.x];
+        t[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) Out[(long long)(bx + r) * Mp + by + threadIdx.x] = t[threadIdx.x][r];
+}
+
+// Out[i,k] = In[i,k] * colscale[k]
+__global__ void colscale_kernel(const double* __restrict__ In, double* __restrict__ Out, int Mp, const double* __restrict__ colscale) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (k < Mp) Out[(long long)i * Mp + k] = In[(long long)i * Mp + k] * colscale[k];
+}
+
+// copy a NB x NB block (ld NB) into a block of a big matrix
+__global__ void copy_block_kernel(const double* __restrict__ src, double* __restrict__ dst, long long ldd) {
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(long long)(e / NB) * ldd + e % NB] = src[e];
+}
+
+// y[i] = sum_k Mat[i,k] * (x[k] - (x2 ? x2[k] : 0)) ; one warp per row.  mode 1: y[i] = sum_k Mat[i,k]^2 ; mode 2: sum_k Mat[i,k]*Mat2[i,k]
+__global__ void rowop_kernel(const double* __restrict__ Mat, const double* __restrict__ Mat2, const double* __restrict__ x,
+                             const double* __restrict__ x2, double* __restrict__ y, int Mp, int mode) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= Mp) return;
+    const double* m = Mat + (long long)row * Mp;
+    double s = 0.0;
+    for (int k = lane; k < Mp; k += 32) {
+        double v = m[k];
+        if (mode == 0) s = fma(v, x[k] - (x2 ? x2[k] : 0.0), s);
+        else if (mode == 1) s = fma(v, v, s);
+        else s = fma(v, Mat2[(long long)row * Mp + k], s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+}
+
+// pad a length-M vector of theta into a length-Mp workspace vector (zeros beyond M)
+__global__ void pad_vec_kernel(const double* __restrict__ src, double* __restrict__ dst, int M, int Mp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Mp) dst[i] = (i < M) ? src[i] : 0.0;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) for (int i = 0; i < nw; i++) s += sh[i];
+    return s;   // valid on thread 0
+}
+
+// KL of one latent (diag branch of onofftf/main.py:187-252 without the extra jitter):
+//   0.5 * [ |aw|^2 - M - sum log s^2 + sum dK*s^2 + sum log L_mm^2 ]
+__global__ void kl_kernel(const double* __restrict__ aw, const double* __restrict__ s, const double* __restrict__ dK,
+                          const double* __restrict__ L, int M, int Mp, double* __restrict__ kl_out) {
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        double lm = L[(long long)m * Mp + m];
+        v += aw[m] * aw[m] - log(s[m] * s[m]) + dK[m] * s[m] * s[m] + log(lm * lm);
+    }
+    double t = block_sum(v, sh);
+    if (threadIdx.x == 0) kl_out[0] = 0.5 * (t - (double)M);
+}
+
+// unpack the reduced accumulator E (lower 128-tiles valid) into a full symmetric matrix
+__global__ void symmetrize_lower_kernel(const double* __restrict__ Elow, double* __restrict__ E, int Mp, int tile) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    double v;
+    if (j <= i) v = Elow[(long long)i * Mp + j];
+    else v = Elow[(long long)j * Mp + i];
+    // inside diagonal tiles both halves were accumulated; they agree up to summation order -- take the lower one
+    (void)tile;
+    E[(long long)i * Mp + j] = v;
+}
+
+// Hs = E - EP - EP^T - (a aw^T + aw a^T)/2 + aw aw^T/2 + P/2 - I/2
+__global__ void hs_kernel(const double* __restrict__ E, const double* __restrict__ EP, const double* __restrict__ P,
+                          const double* __restrict__ a, const double* __restrict__ aw, int Mp, double* __restrict__ Hs) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    long long ij = (long long)i * Mp + j, ji = (long long)j * Mp + i;
+    double v = E[ij] - EP[ij] - EP[ji] - 0.5 * (a[i] * aw[j] + aw[i] * a[j]) + 0.5 * aw[i] * aw[j] + 0.5 * P[ij];
+    if (i == j) v -= 0.5;
+    Hs[ij] = v;
+}
+
+// Kmm-side parameter gradients from G = dELBO/dKmm (symmetric): one block per row i < M.
+//   gZ[i,d]   = -2 sum_j G_ij k_ij (z_id - z_jd) / ell_d^2
+//   pell[i,d] =    sum_j G_ij k_ij (z_id - z_jd)^2 / ell_d^3
+//   pvar[i]   =    sum_j G_ij k_ij / var
+__global__ void __launch_bounds__(128) kmm_grad_kernel(const double* __restrict__ G, const double* __restrict__ Z,
+                                                       const double* __restrict__ ell, const double* __restrict__ var, int M, int D, int Mp,
+                                                       double* __restrict__ gZ, double* __restrict__ pell, double* __restrict__ pvar) {
+    __shared__ double sh[32];
+    const int i = blockIdx.x;
+    double zi[ZIGP_MAX_D], il[ZIGP_MAX_D], az[ZIGP_MAX_D], al[ZIGP_MAX_D];
+#pragma unroll
+    for (int d = 0; d < ZIGP_MAX_D; d++) {
+        zi[d] = (d < D) ? Z[i * D + d] : 0.0;
+        il[d] = (d < D) ? 1.0 / ell[d] : 0.0;
+        az[d] = 0.0; al[d] = 0.0;
+    }
+    double av = 0.0;
+    const double v = var[0];
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        double df[ZIGP_MAX_D];
+        double r2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < ZIGP_MAX_D; d++) {
+            df[d] = (d < D) ? (zi[d] - Z[j * D + d]) : 0.0;
+            double t = df[d] * il[d];
+            r2 = fma(t, t, r2);
+        }
+        double w = G[(long long)i * Mp + j] * v * exp(-0.5 * r2);
+        av += w;
+#pragma unroll
+        for (int d = 0; d < ZIGP_MAX_D; d++) { az[d] = fma(w, df[d], az[d]); al[d] = fma(w * df[d], df[d], al[d]); }
+    }
+    double t = block_sum(av, sh);
+    if (threadIdx.x == 0) pvar[i] = t / v;
+#pragma unroll
+    for (int d = 0; d < ZIGP_MAX_D; d++) {
+        if (d < D) {
+            double tz = block_sum(az[d], sh);
+            double tl = block_sum(al[d], sh);
+            if (threadIdx.x == 0) {
+                gZ[i * D + d] = -2.0 * tz * il[d] * il[d];
+                pell[i * D + d] = tl * il[d] * il[d] * il[d];
+            }
+        }
+    }
+}
+
+}  // namespace zigp

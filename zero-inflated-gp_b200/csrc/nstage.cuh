@@ -1,0 +1,231 @@
+// N-stage kernels that are not contractions: Kmn tile construction, the per-point closed-form on/off likelihood
+// (forward and backward), the Kmn-side kernel-gradient reductions, and the predict epilogue.
+#pragma once
+#include "mstage.cuh"
+
+namespace zigp {
+
+// K[n, m] = var * exp(-0.5 * sum_d ((x_nd - z_md)/ell_d)^2)   for n < nvalid, m < M ; 0 in the padding.
+// Point-major (m contiguous) so that every later contraction reads k-contiguous operands.  (onofftf/main.py:53-57)
+__global__ void __launch_bounds__(256) kgen_kernel(const double* __restrict__ X, const double* __restrict__ Z,
+                                                   const double* __restrict__ ell, const double* __restrict__ var, long long n0,
+                                                   int nvalid, int rows, int M, int D, int Mp, double* __restrict__ K) {
+    __shared__ double sx[8][ZIGP_MAX_D];
+    const int m = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;                 // 8 rows per pass
+    double z[ZIGP_MAX_D], il[ZIGP_MAX_D];
+#pragma unroll
+    for (int d = 0; d < ZIGP_MAX_D; d++) {
+        z[d] = (d < D && m < M) ? Z[m * D + d] : 0.0;
+        il[d] = (d < D) ? 1.0 / ell[d] : 0.0;
+    }
+    const double v = var[0];
+    const int rbeg = blockIdx.y * 64;
+    for (int rr = rbeg; rr < rbeg + 64; rr += 8) {
+        const int r = rr + rl;
+        __syncthreads();
+        if ((threadIdx.x & 31) < D && r < nvalid) sx[rl][threadIdx.x & 31] = X[(n0 + r) * D + (threadIdx.x & 31)];
+        __syncthreads();
+        double out = 0.0;
+        if (r < nvalid && m < M) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < ZIGP_MAX_D; d++) {
+                if (d < D) { double t = (sx[rl][d] - z[d]) * il[d]; r2 = fma(t, t, r2); }
+            }
+            out = v * exp(-0.5 * r2);
+        }
+        if (r < rows) K[(long long)r * Mp + m] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-point closed-form expectations (onoffgpf/OnOffSVGP.py:168-204) and their derivatives
+// ---------------------------------------------------------------------------------------------------------------
+struct PointOut {
+    double e1, e2, ev;          // E[Phi], E[Phi^2]+, Var+ (clipped)
+    double dmf, dvf, dmg, dvg;  // d var_exp / d (fmean, fvar, gmean, gvar)
+    double ll, dnoise;
+};
+
+__device__ __forceinline__ void probit_expectations(double mg, double vg, double& c, double& Tw, double& z, double& a,
+                                                    double& ex, double& at) {
+    const double INV_SQRT2 = 0.70710678118654752440;
+    const double TWO_PI = 6.283185307179586476925;
+    z = mg / sqrt(1.0 + vg);                       // :190
+    a = 1.0 / sqrt(1.0 + 2.0 * vg);                // :191
+    c = 0.5 * (1.0 + erf(z * INV_SQRT2)) * (1.0 - 2.0e-3) + 1.0e-3;   // :177-178
+    ex = exp(-0.5 * (z * z) * (a * a + 1.0));      // :187
+    at = atan(a);
+    Tw = at / TWO_PI * ex;                         // :186-188
+}
+
+__device__ __forceinline__ PointOut point_eval(double mf, double vf, double mg, double vg, double y, double noise) {
+    const double TWO_PI = 6.283185307179586476925;
+    PointOut o;
+    double c, Tw, z, a, ex, at;
+    probit_expectations(mg, vg, c, Tw, z, a, ex, at);
+    const double q2 = c - 2.0 * Tw;                // :197
+    const double qv = c - 2.0 * Tw - c * c;        // :198
+    o.e1 = c;
+    o.e2 = 0.5 * (q2 + fabs(q2));                  // :201
+    o.ev = 0.5 * (qv + fabs(qv));                  // :202
+    const double r = y - o.e1 * mf;
+    const double quad = r * r + o.e2 * vf + o.ev * mf * mf;
+    const double inv_noise = 1.0 / noise;
+    // onoffgpf/OnOffLikelihood.py:31-32
+    o.ll = -0.5 * log(TWO_PI) - 0.5 * log(noise) - 0.5 * quad * inv_noise;
+    o.dmf = (o.e1 * r - o.ev * mf) * inv_noise;
+    o.dvf = -0.5 * o.e2 * inv_noise;
+    const double de1 = mf * r * inv_noise;
+    const double de2 = -0.5 * vf * inv_noise;
+    const double dev = -0.5 * mf * mf * inv_noise;
+    // sub-gradient of (x + |x|)/2 as TF/torch define it: sign(0) = 0 -> 1/2 at x == 0
+    const double i2 = (q2 > 0.0) ? 1.0 : ((q2 < 0.0) ? 0.0 : 0.5);
+    const double iv = (qv > 0.0) ? 1.0 : ((qv < 0.0) ? 0.0 : 0.5);
+    const double dc = de1 + i2 * de2 + iv * dev * (1.0 - 2.0 * c);
+    const double dT = -2.0 * i2 * de2 - 2.0 * iv * dev;
+    const double dcdz = (1.0 - 2.0e-3) * exp(-0.5 * z * z) * 0.39894228040143267794;
+    const double dTdz = -z * (a * a + 1.0) * Tw;
+    const double dTda = ex / TWO_PI * (1.0 / (1.0 + a * a) - z * z * a * at);
+    const double dz = dc * dcdz + dT * dTdz;
+    const double da = dT * dTda;
+    const double i1 = 1.0 / (1.0 + vg), s1 = sqrt(i1);
+    o.dmg = dz * s1;
+    o.dvg = dz * (-0.5 * mg * i1 * s1) - da * a * a * a;     // a^3 = (1+2 vg)^(-3/2)
+    o.dnoise = -0.5 * inv_noise + 0.5 * quad * inv_noise * inv_noise;
+    return o;
+}
+
+struct PointArgs {
+    // per latent: row statistics from the contraction epilogues, [ntc][rows]
+    const double* sqA[2]; const double* dotA[2]; const double* sqRA[2];
+    const double* var[2];       // kernel variances (device scalars)
+    const double* noise;
+    const double* Y; long long n0; int nvalid, rows, ntc[2];
+    double scale;
+    double* mean[2]; double* vr[2];   // fmean/fvar, gmean/gvar
+    double* gm[2]; double* gv[2];     // scale * d var_exp / d mean, d var
+    double* partial;                  // [gridDim.x][4]: sum ll, scale*sum dnoise, sum gv_f, sum gv_g  (+= across chunks)
+};
+
+__global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
+    __shared__ double sh[32];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    double ll = 0.0, dn = 0.0, sgf = 0.0, sgg = 0.0;
+    if (r < p.rows) {
+        double mean[2], vr[2];
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+            double sa = 0.0, da = 0.0, sra = 0.0;
+            for (int t = 0; t < p.ntc[l]; t++) {      // fixed order: deterministic
+                sa += p.sqA[l][(long long)t * p.rows + r];
+                da += p.dotA[l][(long long)t * p.rows + r];
+                sra += p.sqRA[l][(long long)t * p.rows + r];
+            }
+            mean[l] = da;                               // onofftf/main.py:286  (A^T q_mu == A_w^T alpha_w)
+            vr[l] = p.var[l][0] - sa + sra;             // :277 + :301
+            p.mean[l][r] = mean[l];
+            p.vr[l][r] = vr[l];
+        }
+        if (r < p.nvalid) {
+            PointOut o = point_eval(mean[0], vr[0], mean[1], vr[1], p.Y[p.n0 + r], p.noise[0]);
+            ll = o.ll; dn = p.scale * o.dnoise;
+            p.gm[0][r] = p.scale * o.dmf; p.gv[0][r] = p.scale * o.dvf;
+            p.gm[1][r] = p.scale * o.dmg; p.gv[1][r] = p.scale * o.dvg;
+            sgf = p.scale * o.dvf; sgg = p.scale * o.dvg;
+        } else {
+            p.gm[0][r] = 0.0; p.gv[0][r] = 0.0; p.gm[1][r] = 0.0; p.gv[1][r] = 0.0;
+        }
+    }
+    double t0 = block_sum(ll, sh), t1 = block_sum(dn, sh), t2 = block_sum(sgf, sh), t3 = block_sum(sgg, sh);
+    if (threadIdx.x == 0) {
+        double* q = p.partial + (long long)blockIdx.x * 4;
+        q[0] += t0; q[1] += t1; q[2] += t2; q[3] += t3;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kmn-side kernel gradient sums.  With  kbar[n,m] = gm_n * beta_m - 2 gv_n * Y[n,m]  and  G = kbar * K :
+//   S0[m]   += sum_n G              S1[d][m] += sum_n G (x_nd - z_md)        Q[d][m] += sum_n G (x_nd - z_md)^2
+//   a[m]    += sum_n gm_n A[n,m]
+// Block = 128 columns x KG_ROWS rows; partial sums land in slot [blockIdx.y] (owned by this CTA across chunks).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KG_ROWS = 256;
+struct KgradArgs {
+    const double* K; const double* Y; const double* A; long long ld;
+    const double* gm; const double* gv; const double* beta;
+    const double* X; long long n0; int nvalid;
+    const double* Z; int M, D, Mp;
+    double* partial;     // [nslots][2 + 2*D][Mp]
+};
+
+__global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
+    __shared__ double sx[KG_ROWS][ZIGP_MAX_D];
+    __shared__ double sgm[KG_ROWS], sgv[KG_ROWS];
+    const int m = blockIdx.x * 128 + threadIdx.x;
+    const int r0 = blockIdx.y * KG_ROWS;
+    const int nr = min(KG_ROWS, p.nvalid - r0);
+    if (nr <= 0) return;
+    for (int e = threadIdx.x; e < nr * p.D; e += 128) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
+    for (int e = threadIdx.x; e < nr; e += 128) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
+    __syncthreads();
+    double z[ZIGP_MAX_D], s1[ZIGP_MAX_D], q[ZIGP_MAX_D];
+#pragma unroll
+    for (int d = 0; d < ZIGP_MAX_D; d++) { z[d] = (d < p.D && m < p.M) ? p.Z[m * p.D + d] : 0.0; s1[d] = 0.0; q[d] = 0.0; }
+    const double bm = p.beta[m];
+    double s0 = 0.0, am = 0.0;
+    const double* Kp = p.K + (long long)r0 * p.ld + m;
+    const double* Yp = p.Y + (long long)r0 * p.ld + m;
+    const double* Ap = p.A + (long long)r0 * p.ld + m;
+#pragma unroll 4
+    for (int r = 0; r < nr; r++) {
+        const double k = Kp[(long long)r * p.ld], yy = Yp[(long long)r * p.ld], aa = Ap[(long long)r * p.ld];
+        const double G = (sgm[r] * bm - 2.0 * sgv[r] * yy) * k;
+        s0 += G;
+        am = fma(sgm[r], aa, am);
+#pragma unroll
+        for (int d = 0; d < ZIGP_MAX_D; d++) {
+            if (d < p.D) { double df = sx[r][d] - z[d]; s1[d] = fma(G, df, s1[d]); q[d] = fma(G * df, df, q[d]); }
+        }
+    }
+    double* out = p.partial + (long long)blockIdx.y * (2 + 2 * p.D) * p.Mp + m;
+    out[0] += s0;
+    out[(long long)p.Mp] += am;
+#pragma unroll
+    for (int d = 0; d < ZIGP_MAX_D; d++) {
+        if (d < p.D) { out[(long long)(2 + d) * p.Mp] += s1[d]; out[(long long)(2 + p.D + d) * p.Mp] += q[d]; }
+    }
+}
+
+// reduce slots: dst[i] = sum_s src[s*stride + i]  (fixed order)
+__global__ void reduce_slots_kernel(const double* __restrict__ src, long long stride, int nslots, double* __restrict__ dst, long long len) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double s = 0.0;
+    for (int k = 0; k < nslots; k++) s += src[(long long)k * stride + i];
+    dst[i] = s;
+}
+
+// predict epilogue: the 9 outputs of build_predict (onoffgpf/OnOffSVGP.py:140-152) from the four moments
+__global__ void predict_kernel(const double* __restrict__ mf, const double* __restrict__ vf, const double* __restrict__ mg,
+                               const double* __restrict__ vg, int nvalid, long long n0, long long ntot, double* __restrict__ out9) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nvalid) return;
+    double c, Tw, z, a, ex, at;
+    probit_expectations(mg[r], vg[r], c, Tw, z, a, ex, at);
+    const double q2 = c - 2.0 * Tw, qv = c - 2.0 * Tw - c * c;
+    const double e2 = 0.5 * (q2 + fabs(q2)), ev = 0.5 * (qv + fabs(qv));
+    const long long i = n0 + r;
+    out9[0 * ntot + i] = c * mf[r];
+    out9[1 * ntot + i] = e2 * vf[r];
+    out9[2 * ntot + i] = ev * mf[r] * mf[r];
+    out9[3 * ntot + i] = mf[r];
+    out9[4 * ntot + i] = vf[r];
+    out9[5 * ntot + i] = mg[r];
+    out9[6 * ntot + i] = vg[r];
+    out9[7 * ntot + i] = c;
+    out9[8 * ntot + i] = ev;
+}
+
+}  // namespace zigp

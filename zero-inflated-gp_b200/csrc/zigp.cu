@@ -1,0 +1,631 @@
+// libzigp: context, orchestration and the C ABI declared in include/zigp.h.
+// Pipeline per evaluation:
+//   M-stage forward (per latent)  ->  chunks of points: Kmn tile -> A = T k -> RA = R A -> V = A - R^T RA -> Y = T^T V
+//   -> per-point likelihood fwd/bwd -> Kmn-side gradient sums + whitened statistic E += A^T diag(gv) A
+//   -> [allreduce of the packed accumulator across ranks, done by the caller] -> M-stage backward -> packed output.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "nstage.cuh"
+
+using namespace zigp;
+
+namespace {
+
+constexpr int BMN = 128;       // N-stage tile (rows and columns)
+thread_local std::string g_create_error;
+
+struct Latent {
+    int M = 0, Mp = 0, nb = 0, ntc = 0;
+    long long off_ell = 0, off_var = 0, off_Z = 0, off_mu = 0, off_s = 0;
+    // M-stage
+    double *Lb = nullptr, *Lt = nullptr, *T = nullptr, *Tt = nullptr, *Rt = nullptr, *R = nullptr;
+    double *Dinv = nullptr, *Dinvt = nullptr, *Xtmp = nullptr;
+    double *mu = nullptr, *s = nullptr, *aw = nullptr, *beta = nullptr, *dK = nullptr, *kl = nullptr;
+    // backward
+    double *E = nullptr, *P = nullptr, *EP = nullptr, *Hs = nullptr, *Ut = nullptr, *G = nullptr, *ETt = nullptr;
+    double *dE = nullptr, *gmu = nullptr, *gZmm = nullptr, *pell = nullptr, *pvar = nullptr;
+    // N-stage (per chunk)
+    double *Kb = nullptr, *Ab = nullptr, *RAb = nullptr, *Vb = nullptr;
+    double *sqA = nullptr, *dotA = nullptr, *sqRA = nullptr;
+    double *mean = nullptr, *vr = nullptr, *gm = nullptr, *gv = nullptr;
+    double *kg_partial = nullptr, *E_splits = nullptr;
+    int nsplit = 1;
+    // accumulator views
+    double *accE = nullptr, *accV = nullptr;
+};
+
+}  // namespace
+
+struct zigp_ctx {
+    int device = 0, D = 0;
+    double jitter = 1e-6;
+    long long chunk = 0;          // rows per chunk (multiple of 512)
+    Latent lat[2];
+    long long theta_len = 0;
+    // data
+    const double* X = nullptr; const double* Y = nullptr;
+    double *Xown = nullptr, *Yown = nullptr; long long own_cap = 0;
+    long long n_local = 0; double scale = 1.0; bool has_data = false;
+    // accumulators
+    double* accum = nullptr; long long accum_len = 0;
+    double* pt_partial = nullptr; int pt_slots = 0; int kg_slots = 0;
+    int* info = nullptr;
+    // host staging
+    double *theta_dev = nullptr, *out_dev = nullptr, *theta_pin = nullptr, *out_pin = nullptr;
+    std::vector<void*> allocs;
+    std::string err;
+    long long launches = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            char b_[512];                                                                                  \
+            snprintf(b_, sizeof b_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+            c->err = b_;                                                                                   \
+            return ZIGP_ECUDA;                                                                             \
+        }                                                                                                  \
+    } while (0)
+
+#define LAUNCHED()                                 \
+    do {                                           \
+        c->launches++;                             \
+        CK(cudaGetLastError());                    \
+    } while (0)
+
+inline long long rup(long long x, long long a) { return (x + a - 1) / a * a; }
+
+int dalloc(zigp_ctx* c, double** p, long long n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, (size_t)std::max<long long>(n, 1) * sizeof(double)));
+    CK(cudaMemset(q, 0, (size_t)std::max<long long>(n, 1) * sizeof(double)));
+    c->allocs.push_back(q);
+    *p = (double*)q;
+    return 0;
+}
+#define DA(ptr, n)                                    \
+    do {                                              \
+        int r_ = dalloc(c, &(ptr), (n));              \
+        if (r_) return r_;                            \
+    } while (0)
+
+using GemmN = TnCfg<BMN, BMN, 64, 32, 4>;
+
+int gemmN(zigp_ctx* c, const GemmArgs& g, cudaStream_t st) {
+    CK((launch_gemm_tn<BMN, BMN, 64, 32, 4>(g, st)));
+    c->launches++;
+    return 0;
+}
+int gemmM(zigp_ctx* c, const double* In, long long ldi, const double* W, long long ldw, double* Out, long long ldo, const double* Zin,
+          long long ldz, double alpha, double beta, int rows, int cols, int kdim, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0 || kdim <= 0) return 0;
+    GemmArgs g{};
+    g.In = In; g.ldi = ldi; g.W = W; g.ldw = ldw; g.Out = Out; g.ldo = ldo; g.Zin = Zin; g.ldz = ldz;
+    g.alpha = alpha; g.beta = beta; g.rows = rows; g.cols = cols; g.kdim = kdim; g.tri = TRI_FULL;
+    CK((launch_gemm_tn<NB, NB, 32, 32, 4>(g, st)));
+    c->launches++;
+    return 0;
+}
+#define RUN(expr)                \
+    do {                         \
+        int r_ = (expr);         \
+        if (r_) return r_;       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
+    Latent& L = c->lat[l];
+    const int M = L.M, Mp = L.Mp, D = c->D;
+    const long long MM = (long long)Mp * Mp;
+    dim3 g2((Mp + 127) / 128, Mp);
+    kmm_build_kernel<<<g2, 128, 0, st>>>(theta + L.off_Z, theta + L.off_ell, theta + L.off_var, M, D, Mp, c->jitter, L.Lb);
+    LAUNCHED();
+    pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_mu, L.mu, M, Mp);
+    LAUNCHED();
+    pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_s, L.s, M, Mp);
+    LAUNCHED();
+    // blocked right-looking Cholesky
+    for (int kb = 0; kb < L.nb; kb++) {
+        double* diag = L.Lb + (long long)kb * NB * (Mp + 1);
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, L.Dinv + (long long)kb * NB * NB, L.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, l);
+        LAUNCHED();
+        const int rem = Mp - (kb + 1) * NB;
+        if (rem > 0) {
+            double* panel = L.Lb + (long long)(kb + 1) * NB * Mp + (long long)kb * NB;
+            RUN(gemmM(c, panel, Mp, L.Dinv + (long long)kb * NB * NB, NB, panel, Mp, nullptr, 0, 1.0, 0.0, rem, NB, NB, st));
+            double* trail = L.Lb + (long long)(kb + 1) * NB * (Mp + 1);
+            RUN(gemmM(c, panel, Mp, panel, Mp, trail, Mp, trail, Mp, -1.0, 1.0, rem, rem, NB, st));
+        }
+    }
+    zero_upper_kernel<<<g2, 128, 0, st>>>(L.Lb, Mp);
+    LAUNCHED();
+    dim3 gt(Mp / 32, Mp / 32), bt(32, 8);
+    transpose_kernel<<<gt, bt, 0, st>>>(L.Lb, L.Lt, Mp, nullptr);
+    LAUNCHED();
+    // T = L^-1 by block columns, last to first
+    CK(cudaMemsetAsync(L.T, 0, MM * sizeof(double), st));
+    for (int jb = L.nb - 1; jb >= 0; jb--) {
+        copy_block_kernel<<<1, 256, 0, st>>>(L.Dinv + (long long)jb * NB * NB, L.T + (long long)jb * NB * (Mp + 1), Mp);
+        LAUNCHED();
+        const int i0 = (jb + 1) * NB, rem = Mp - i0;
+        if (rem > 0) {
+            RUN(gemmM(c, L.T + (long long)i0 * Mp + i0, Mp, L.Lt + (long long)jb * NB * Mp + i0, Mp, L.Xtmp, NB, nullptr, 0, 1.0, 0.0, rem, NB, rem, st));
+            RUN(gemmM(c, L.Xtmp, NB, L.Dinvt + (long long)jb * NB * NB, NB, L.T + (long long)i0 * Mp + (long long)jb * NB, Mp, nullptr, 0, -1.0, 0.0, rem, NB, NB, st));
+        }
+    }
+    transpose_kernel<<<gt, bt, 0, st>>>(L.T, L.Tt, Mp, nullptr);
+    LAUNCHED();
+    colscale_kernel<<<g2, 128, 0, st>>>(L.T, L.Rt, Mp, L.s);
+    LAUNCHED();
+    transpose_kernel<<<gt, bt, 0, st>>>(L.Rt, L.R, Mp, nullptr);
+    LAUNCHED();
+    const int rb = (Mp + 7) / 8;
+    rowop_kernel<<<rb, 256, 0, st>>>(L.T, nullptr, L.mu, nullptr, L.aw, Mp, 0);
+    LAUNCHED();
+    rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, L.aw, nullptr, L.beta, Mp, 0);
+    LAUNCHED();
+    rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, nullptr, nullptr, L.dK, Mp, 1);
+    LAUNCHED();
+    kl_kernel<<<1, 256, 0, st>>>(L.aw, L.s, L.dK, L.Lb, M, Mp, L.kl);
+    LAUNCHED();
+    return 0;
+}
+
+// forward contractions of one chunk for one latent: K, A (+stats), RA (+stats); optionally V, Y for the backward
+int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long long n0, int nvalid, int rows, bool need_bwd, cudaStream_t st) {
+    Latent& L = c->lat[l];
+    const int Mp = L.Mp;
+    dim3 gk(Mp / 32, rows / 64);
+    kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb);
+    LAUNCHED();
+    GemmArgs g{};
+    g.rows = rows; g.cols = Mp; g.kdim = Mp; g.alpha = 1.0; g.beta = 0.0;
+    // A[n,m] = sum_{k<=m} K[n,k] T[m,k]           (onofftf/main.py:270, A = Lm^-1 Kmn)
+    g.In = L.Kb; g.ldi = Mp; g.W = L.T; g.ldw = Mp; g.Out = L.Ab; g.ldo = Mp; g.tri = TRI_LOWER;
+    g.stat_sq = L.sqA; g.stat_dot = L.dotA; g.dotvec = L.aw;
+    RUN(gemmN(c, g, st));
+    // RA[n,m] = sum_{k>=m} A[n,k] R[m,k],  R = diag(s) T^T    (main.py:283 + :290 fused: (Lm^-T A) * q_sqrt)
+    g.In = L.Ab; g.W = L.R; g.Out = L.RAb; g.tri = TRI_UPPER;
+    g.stat_sq = L.sqRA; g.stat_dot = nullptr; g.dotvec = nullptr;
+    RUN(gemmN(c, g, st));
+    if (need_bwd) {
+        // V = A - R^T RA :  V[n,m] = A[n,m] - sum_{k<=m} RA[n,k] Rt[m,k]
+        g.In = L.RAb; g.W = L.Rt; g.Out = L.Vb; g.tri = TRI_LOWER; g.alpha = -1.0; g.beta = 1.0; g.Zin = L.Ab; g.ldz = Mp;
+        g.stat_sq = nullptr;
+        RUN(gemmN(c, g, st));
+        // Y = T^T V :  Y[n,m] = sum_{k>=m} V[n,k] Tt[m,k]      (overwrites RA, which is dead)
+        g.In = L.Vb; g.W = L.Tt; g.Out = L.RAb; g.tri = TRI_UPPER; g.alpha = 1.0; g.beta = 0.0; g.Zin = nullptr;
+        RUN(gemmN(c, g, st));
+    }
+    return 0;
+}
+
+int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long long n0, int nvalid, int rows, cudaStream_t st) {
+    PointArgs p{};
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        p.sqA[l] = L.sqA; p.dotA[l] = L.dotA; p.sqRA[l] = L.sqRA; p.var[l] = theta + L.off_var; p.ntc[l] = L.ntc;
+        p.mean[l] = L.mean; p.vr[l] = L.vr; p.gm[l] = L.gm; p.gv[l] = L.gv;
+    }
+    p.noise = theta + 2 * c->D + 2;
+    p.Y = Y; p.n0 = n0; p.nvalid = Y ? nvalid : 0; p.rows = rows; p.scale = c->scale; p.partial = c->pt_partial;
+    point_kernel<<<rows / 256, 256, 0, st>>>(p);
+    LAUNCHED();
+    return 0;
+}
+
+int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
+    if (!c->has_data) { c->err = "zigp: no data set (call zigp_set_data_* first)"; return ZIGP_ESTATE; }
+    CK(cudaSetDevice(c->device));
+    const int D = c->D;
+    CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(c->pt_partial, 0, (size_t)c->pt_slots * 4 * sizeof(double), st));
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        CK(cudaMemsetAsync(L.E_splits, 0, (size_t)L.nsplit * L.Mp * L.Mp * sizeof(double), st));
+        CK(cudaMemsetAsync(L.kg_partial, 0, (size_t)c->kg_slots * (2 + 2 * D) * L.Mp * sizeof(double), st));
+        RUN(mstage_forward(c, l, theta, st));
+    }
+    for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
+        const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
+        const int rows = (int)rup(nvalid, 512);
+        for (int l = 0; l < 2; l++) RUN(chunk_forward(c, l, theta, c->X, n0, nvalid, rows, true, st));
+        RUN(run_point_kernel(c, theta, c->Y, n0, nvalid, rows, st));
+        for (int l = 0; l < 2; l++) {
+            Latent& L = c->lat[l];
+            KgradArgs k{};
+            k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
+            k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
+            dim3 gg(L.Mp / 128, (nvalid + KG_ROWS - 1) / KG_ROWS);
+            kgrad_kernel<<<gg, 128, 0, st>>>(k);
+            LAUNCHED();
+            SyrkArgs s{};
+            s.A = L.Ab; s.lda = L.Mp; s.w = L.gv; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
+            s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
+            CK((launch_syrk_nt<BMN, 64, 32, 3>(s, st)));
+            c->launches++;
+        }
+    }
+    // fold the per-CTA slots into the packed accumulator (fixed order -> deterministic)
+    reduce_slots_kernel<<<1, 32, 0, st>>>(c->pt_partial, 4, c->pt_slots, c->accum, 4);
+    LAUNCHED();
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        long long MM = (long long)L.Mp * L.Mp;
+        reduce_slots_kernel<<<(unsigned)((MM + 255) / 256), 256, 0, st>>>(L.E_splits, MM, L.nsplit, L.accE, MM);
+        LAUNCHED();
+        long long VL = (long long)(2 + 2 * D) * L.Mp;
+        reduce_slots_kernel<<<(unsigned)((VL + 255) / 256), 256, 0, st>>>(L.kg_partial, VL, c->kg_slots, L.accV, VL);
+        LAUNCHED();
+    }
+    return 0;
+}
+
+// assemble the packed output (one block)
+struct FinalArgs {
+    const double* theta; double* out; const double* accum; const int* info;
+    double scale; int D;
+    struct Lat {
+        int M, Mp; long long off_ell, off_var, off_Z, off_mu, off_s;
+        const double *accV, *gZmm, *pell, *pvar, *gmu, *dE, *dK, *s, *kl;
+    } lat[2];
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs f) {
+    __shared__ double sh[32];
+    const int D = f.D;
+    double* grad = f.out + ZIGP_OUT_HEADER;
+    for (int l = 0; l < 2; l++) {
+        const FinalArgs::Lat& L = f.lat[l];
+        const double* S0 = L.accV;
+        const double* S1 = L.accV + (long long)2 * L.Mp;
+        const double* Q = L.accV + (long long)(2 + D) * L.Mp;
+        const double var = f.theta[L.off_var];
+        // variance
+        double v = 0.0;
+        for (int m = threadIdx.x; m < L.M; m += blockDim.x) v += S0[m] / var + L.pvar[m];
+        double t = block_sum(v, sh);
+        if (threadIdx.x == 0) grad[L.off_var] = t + f.accum[2 + l];
+        for (int d = 0; d < D; d++) {
+            const double ell = f.theta[L.off_ell + d];
+            double w = 0.0;
+            for (int m = threadIdx.x; m < L.M; m += blockDim.x) w += Q[(long long)d * L.Mp + m] / (ell * ell * ell) + L.pell[m * D + d];
+            double t2 = block_sum(w, sh);
+            if (threadIdx.x == 0) grad[L.off_ell + d] = t2;
+            for (int m = threadIdx.x; m < L.M; m += blockDim.x)
+                grad[L.off_Z + (long long)m * D + d] = S1[(long long)d * L.Mp + m] / (ell * ell) + L.gZmm[m * D + d];
+        }
+        for (int m = threadIdx.x; m < L.M; m += blockDim.x) {
+            const double s = L.s[m];
+            grad[L.off_mu + m] = L.gmu[m];
+            grad[L.off_s + m] = 2.0 * s * L.dE[m] + 1.0 / s - s * L.dK[m];
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double kl = f.lat[0].kl[0] + f.lat[1].kl[0];
+        f.out[0] = f.scale * f.accum[0] - kl;
+        f.out[1] = f.accum[0];
+        f.out[2] = kl;
+        f.out[3] = (double)f.info[0];
+        grad[2 * D + 2] = f.accum[1];
+    }
+}
+
+int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
+    CK(cudaSetDevice(c->device));
+    const int D = c->D;
+    FinalArgs f{};
+    f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.D = D;
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        const int Mp = L.Mp;
+        dim3 g2((Mp + 127) / 128, Mp);
+        const double* a = L.accV + Mp;     // second row of the vector block
+        symmetrize_lower_kernel<<<g2, 128, 0, st>>>(L.accE, L.E, Mp, BMN);
+        LAUNCHED();
+        RUN(gemmM(c, L.Rt, Mp, L.Rt, Mp, L.P, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));       // P = R^T R
+        RUN(gemmM(c, L.E, Mp, L.P, Mp, L.EP, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));          // EP
+        hs_kernel<<<g2, 128, 0, st>>>(L.E, L.EP, L.P, a, L.aw, Mp, L.Hs);
+        LAUNCHED();
+        RUN(gemmM(c, L.Tt, Mp, L.Hs, Mp, L.Ut, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));        // Ut = (Hs T)^T
+        RUN(gemmM(c, L.Tt, Mp, L.Ut, Mp, L.G, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));         // G = T^T Hs T
+        kmm_grad_kernel<<<L.M, 128, 0, st>>>(L.G, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, L.M, D, Mp, L.gZmm, L.pell, L.pvar);
+        LAUNCHED();
+        RUN(gemmM(c, L.Tt, Mp, L.E, Mp, L.ETt, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));        // (E T)^T
+        const int rb = (Mp + 7) / 8;
+        rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, L.ETt, nullptr, nullptr, L.dE, Mp, 2);              // diag(T^T E T)
+        LAUNCHED();
+        rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, a, L.aw, L.gmu, Mp, 0);                    // T^T (a - alpha_w)
+        LAUNCHED();
+        FinalArgs::Lat& q = f.lat[l];
+        q.M = L.M; q.Mp = Mp; q.off_ell = L.off_ell; q.off_var = L.off_var; q.off_Z = L.off_Z; q.off_mu = L.off_mu; q.off_s = L.off_s;
+        q.accV = L.accV; q.gZmm = L.gZmm; q.pell = L.pell; q.pvar = L.pvar; q.gmu = L.gmu; q.dE = L.dE; q.dK = L.dK; q.s = L.s; q.kl = L.kl;
+    }
+    finalize_kernel<<<1, 256, 0, st>>>(f);
+    LAUNCHED();
+    return 0;
+}
+
+__global__ void kl_out_kernel(const double* klf, const double* klg, const int* info, double* out) {
+    out[0] = klf[0] + klg[0];
+    out[1] = (double)info[0];
+}
+
+int ensure_chunk_buffers(zigp_ctx* c) {
+    // N-stage buffers are sized for c->chunk rows at creation; nothing to do (kept for symmetry / future resizing)
+    (void)c;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows) {
+    if (!out) return ZIGP_EINVAL;
+    *out = nullptr;
+    if (Mf <= 0 || Mg <= 0 || D <= 0 || D > ZIGP_MAX_D || !(jitter >= 0.0) || Mf >= (1 << 20) || Mg >= (1 << 20)) {
+        g_create_error = "zigp_create: bad argument (need 0 < M < 2^20, 0 < D <= 8, jitter >= 0)";
+        return ZIGP_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = std::string("zigp_create: no usable CUDA device (") + cudaGetErrorString(e) + "); libzigp has no CPU fallback";
+        return ZIGP_ECUDA;
+    }
+    zigp_ctx* c = new zigp_ctx();
+    c->device = device; c->D = D; c->jitter = jitter;
+    auto fail = [&](int code) { g_create_error = c->err; zigp_destroy(c); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(ZIGP_ECUDA); }
+    int cc_major = 0;
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    if (cc_major != 10) { c->err = "libzigp is built for sm_100a (B200) only"; return fail(ZIGP_ECUDA); }
+
+    const int Ms[2] = {Mf, Mg};
+    long long off = 2 * D + 3;
+    c->lat[0].off_ell = 0; c->lat[0].off_var = D; c->lat[1].off_ell = D + 1; c->lat[1].off_var = 2 * D + 1;
+    for (int l = 0; l < 2; l++) { c->lat[l].M = Ms[l]; c->lat[l].off_Z = off; off += (long long)Ms[l] * D; }
+    for (int l = 0; l < 2; l++) { c->lat[l].off_mu = off; off += Ms[l]; }
+    for (int l = 0; l < 2; l++) { c->lat[l].off_s = off; off += Ms[l]; }
+    c->theta_len = off;
+
+    long long chunk = chunk_rows > 0 ? chunk_rows : 32768;
+    chunk = rup(chunk, 512);
+    c->chunk = chunk;
+    c->pt_slots = (int)(chunk / 256);
+    c->kg_slots = (int)((chunk + KG_ROWS - 1) / KG_ROWS);
+
+    // packed accumulator: header(4) + per latent [E (Mp^2), vec block (2+2D) Mp]
+    long long acc_len = 4;
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        L.Mp = (int)rup(L.M, BMN); L.nb = L.Mp / NB; L.ntc = L.Mp / BMN;
+        acc_len += (long long)L.Mp * L.Mp + (long long)(2 + 2 * D) * L.Mp;
+    }
+    c->accum_len = acc_len;
+    { int r = dalloc(c, &c->accum, acc_len); if (r) return fail(r); }
+    long long pos = 4;
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        L.accE = c->accum + pos; pos += (long long)L.Mp * L.Mp;
+        L.accV = c->accum + pos; pos += (long long)(2 + 2 * D) * L.Mp;
+    }
+    auto alloc_all = [&]() -> int {
+        DA(c->pt_partial, (long long)c->pt_slots * 4);
+        void* q = nullptr;
+        CK(cudaMalloc(&q, 16)); c->allocs.push_back(q); c->info = (int*)q;
+        CK(cudaMemset(q, 0, 16));
+        DA(c->theta_dev, c->theta_len);
+        DA(c->out_dev, c->theta_len + ZIGP_OUT_HEADER);
+        CK(cudaMallocHost((void**)&c->theta_pin, (size_t)c->theta_len * sizeof(double)));
+        CK(cudaMallocHost((void**)&c->out_pin, (size_t)(c->theta_len + ZIGP_OUT_HEADER) * sizeof(double)));
+        for (int l = 0; l < 2; l++) {
+            Latent& L = c->lat[l];
+            const long long Mp = L.Mp, MM = Mp * Mp;
+            DA(L.Lb, MM); DA(L.Lt, MM); DA(L.T, MM); DA(L.Tt, MM); DA(L.Rt, MM); DA(L.R, MM);
+            DA(L.Dinv, (long long)L.nb * NB * NB); DA(L.Dinvt, (long long)L.nb * NB * NB); DA(L.Xtmp, Mp * NB);
+            DA(L.mu, Mp); DA(L.s, Mp); DA(L.aw, Mp); DA(L.beta, Mp); DA(L.dK, Mp); DA(L.kl, 2);
+            DA(L.E, MM); DA(L.P, MM); DA(L.EP, MM); DA(L.Hs, MM); DA(L.Ut, MM); DA(L.G, MM); DA(L.ETt, MM);
+            DA(L.dE, Mp); DA(L.gmu, Mp); DA(L.gZmm, Mp * D); DA(L.pell, Mp * D); DA(L.pvar, Mp);
+            DA(L.Kb, chunk * Mp); DA(L.Ab, chunk * Mp); DA(L.RAb, chunk * Mp); DA(L.Vb, chunk * Mp);
+            DA(L.sqA, (long long)L.ntc * chunk); DA(L.dotA, (long long)L.ntc * chunk); DA(L.sqRA, (long long)L.ntc * chunk);
+            DA(L.mean, chunk); DA(L.vr, chunk); DA(L.gm, chunk); DA(L.gv, chunk);
+            DA(L.kg_partial, (long long)c->kg_slots * (2 + 2 * D) * Mp);
+            // SYRK split count: fill the 148 SMs with (lower tiles) x (splits); each split a multiple of 16 rows of a 512-multiple
+            const int tiles = L.ntc * (L.ntc + 1) / 2;
+            int ns = 1;
+            while (ns < 32 && tiles * ns < 148) ns *= 2;
+            L.nsplit = ns;
+            DA(L.E_splits, (long long)ns * MM);
+        }
+        return 0;
+    };
+    { int r = alloc_all(); if (r) return fail(r); }
+    if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
+        c->err = "cudaFuncSetAttribute(potrf_diag_kernel) failed";
+        return fail(ZIGP_ECUDA);
+    }
+    *out = c;
+    return ZIGP_OK;
+}
+
+int zigp_destroy(zigp_ctx* c) {
+    if (!c) return ZIGP_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->Xown) cudaFree(c->Xown);
+    if (c->Yown) cudaFree(c->Yown);
+    if (c->theta_pin) cudaFreeHost(c->theta_pin);
+    if (c->out_pin) cudaFreeHost(c->out_pin);
+    delete c;
+    return ZIGP_OK;
+}
+
+const char* zigp_last_error(const zigp_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+int64_t zigp_theta_len(const zigp_ctx* c) { return c ? c->theta_len : 0; }
+int64_t zigp_launch_count(const zigp_ctx* c) { return c ? c->launches : 0; }
+
+int zigp_set_data_dev(zigp_ctx* c, const double* X, const double* Y, int64_t n, double scale) {
+    if (!c) return ZIGP_EINVAL;
+    if (!X || !Y || n <= 0 || !(scale > 0.0)) { c->err = "zigp_set_data: bad argument"; return ZIGP_EINVAL; }
+    c->X = X; c->Y = Y; c->n_local = n; c->scale = scale; c->has_data = true;
+    return ZIGP_OK;
+}
+
+int zigp_set_data_host(zigp_ctx* c, const double* X, const double* Y, int64_t n, double scale, void* stream) {
+    if (!c) return ZIGP_EINVAL;
+    if (!X || !Y || n <= 0 || !(scale > 0.0)) { c->err = "zigp_set_data: bad argument"; return ZIGP_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > c->own_cap) {
+        CK(cudaStreamSynchronize(st));
+        if (c->Xown) cudaFree(c->Xown);
+        if (c->Yown) cudaFree(c->Yown);
+        c->Xown = c->Yown = nullptr; c->own_cap = 0;
+        CK(cudaMalloc((void**)&c->Xown, (size_t)n * c->D * sizeof(double)));
+        CK(cudaMalloc((void**)&c->Yown, (size_t)n * sizeof(double)));
+        c->own_cap = n;
+    }
+    CK(cudaMemcpyAsync(c->Xown, X, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->Yown, Y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    c->X = c->Xown; c->Y = c->Yown; c->n_local = n; c->scale = scale; c->has_data = true;
+    return ZIGP_OK;
+}
+
+int zigp_accumulate_dev(zigp_ctx* c, const double* theta, void* stream) {
+    if (!c || !theta) return ZIGP_EINVAL;
+    return accumulate(c, theta, (cudaStream_t)stream);
+}
+
+int zigp_accum_buffer(zigp_ctx* c, double** buf, int64_t* len) {
+    if (!c || !buf || !len) return ZIGP_EINVAL;
+    *buf = c->accum; *len = c->accum_len;
+    return ZIGP_OK;
+}
+
+int zigp_finish_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
+    if (!c || !theta || !out) return ZIGP_EINVAL;
+    return finish(c, theta, out, (cudaStream_t)stream);
+}
+
+int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
+    if (!c || !theta || !out) return ZIGP_EINVAL;
+    RUN(accumulate(c, theta, (cudaStream_t)stream));
+    return finish(c, theta, out, (cudaStream_t)stream);
+}
+
+int zigp_elbo_grad_host(zigp_ctx* c, const double* theta, double* out, void* stream) {
+    if (!c || !theta || !out) return ZIGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    memcpy(c->theta_pin, theta, (size_t)c->theta_len * sizeof(double));
+    CK(cudaMemcpyAsync(c->theta_dev, c->theta_pin, (size_t)c->theta_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    RUN(accumulate(c, c->theta_dev, st));
+    RUN(finish(c, c->theta_dev, c->out_dev, st));
+    CK(cudaMemcpyAsync(c->out_pin, c->out_dev, (size_t)(c->theta_len + ZIGP_OUT_HEADER) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out, c->out_pin, (size_t)(c->theta_len + ZIGP_OUT_HEADER) * sizeof(double));
+    if (out[3] != 0.0) {
+        char b[160];
+        long long k = (long long)out[3] - 1;
+        snprintf(b, sizeof b, "zigp: Kmm + jitter*I of latent %s is not positive definite (pivot %lld)", (k >> 20) ? "g" : "f", k & ((1 << 20) - 1));
+        c->err = b;
+        return ZIGP_ENOTPD;
+    }
+    return ZIGP_OK;
+}
+
+int zigp_prior_kl_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
+    if (!c || !theta || !out) return ZIGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+    for (int l = 0; l < 2; l++) RUN(mstage_forward(c, l, theta, st));
+    kl_out_kernel<<<1, 1, 0, st>>>(c->lat[0].kl, c->lat[1].kl, c->info, out);
+    LAUNCHED();
+    return ZIGP_OK;
+}
+
+int zigp_predict_dev(zigp_ctx* c, const double* theta, const double* Xnew, int64_t n_new, double* out9, void* stream) {
+    if (!c || !theta || !Xnew || !out9 || n_new <= 0) return ZIGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
+    for (int l = 0; l < 2; l++) RUN(mstage_forward(c, l, theta, st));
+    for (long long n0 = 0; n0 < n_new; n0 += c->chunk) {
+        const int nvalid = (int)std::min<long long>(c->chunk, n_new - n0);
+        const int rows = (int)rup(nvalid, 512);
+        for (int l = 0; l < 2; l++) RUN(chunk_forward(c, l, theta, Xnew, n0, nvalid, rows, false, st));
+        RUN(run_point_kernel(c, theta, nullptr, n0, nvalid, rows, st));
+        predict_kernel<<<(nvalid + 255) / 256, 256, 0, st>>>(c->lat[0].mean, c->lat[0].vr, c->lat[1].mean, c->lat[1].vr, nvalid, n0, n_new, out9);
+        LAUNCHED();
+    }
+    return ZIGP_OK;
+}
+
+int zigp_predict_host(zigp_ctx* c, const double* theta, const double* Xnew, int64_t n_new, double* out9, void* stream) {
+    if (!c || !theta || !Xnew || !out9 || n_new <= 0) return ZIGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    double *xd = nullptr, *od = nullptr;
+    CK(cudaMalloc((void**)&xd, (size_t)n_new * c->D * sizeof(double)));
+    if (cudaMalloc((void**)&od, (size_t)n_new * 9 * sizeof(double)) != cudaSuccess) { cudaFree(xd); c->err = "cudaMalloc failed in zigp_predict_host"; return ZIGP_ECUDA; }
+    int rc = ZIGP_OK;
+    auto body = [&]() -> int {
+        CK(cudaMemcpyAsync(c->theta_dev, theta, (size_t)c->theta_len * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(xd, Xnew, (size_t)n_new * c->D * sizeof(double), cudaMemcpyHostToDevice, st));
+        RUN(zigp_predict_dev(c, c->theta_dev, xd, n_new, od, stream));
+        CK(cudaMemcpyAsync(out9, od, (size_t)n_new * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return ZIGP_OK;
+    };
+    rc = body();
+    cudaFree(xd); cudaFree(od);
+    return rc;
+}
+
+int zigp_debug_buffer(zigp_ctx* c, const char* name, int latent, double** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
+    if (!c || !name || latent < 0 || latent > 1 || !ptr || !rows || !cols || !ld) return ZIGP_EINVAL;
+    Latent& L = c->lat[latent];
+    const std::string n(name);
+    struct Ent { const char* nm; double* p; long long r, cdim, ldim; };
+    const long long Mp = L.Mp, ch = c->chunk;
+    const Ent tab[] = {
+        {"L", L.Lb, Mp, Mp, Mp}, {"T", L.T, Mp, Mp, Mp}, {"Tt", L.Tt, Mp, Mp, Mp}, {"R", L.R, Mp, Mp, Mp}, {"Rt", L.Rt, Mp, Mp, Mp},
+        {"alpha_w", L.aw, 1, Mp, Mp}, {"beta", L.beta, 1, Mp, Mp}, {"dK", L.dK, 1, Mp, Mp}, {"kl", L.kl, 1, 1, 1},
+        {"E", L.E, Mp, Mp, Mp}, {"accE", L.accE, Mp, Mp, Mp}, {"accV", L.accV, 2 + 2 * c->D, Mp, Mp}, {"G", L.G, Mp, Mp, Mp},
+        {"Hs", L.Hs, Mp, Mp, Mp}, {"P", L.P, Mp, Mp, Mp},
+        {"K", L.Kb, ch, Mp, Mp}, {"A", L.Ab, ch, Mp, Mp}, {"Y", L.RAb, ch, Mp, Mp}, {"V", L.Vb, ch, Mp, Mp},
+        {"mean", L.mean, 1, ch, ch}, {"var", L.vr, 1, ch, ch}, {"gm", L.gm, 1, ch, ch}, {"gv", L.gv, 1, ch, ch},
+    };
+    for (const Ent& e : tab)
+        if (n == e.nm) { *ptr = e.p; *rows = e.r; *cols = e.cdim; *ld = e.ldim; return ZIGP_OK; }
+    c->err = "zigp_debug_buffer: unknown buffer name";
+    return ZIGP_EINVAL;
+}
+
+int zigp_flop_counts(const zigp_ctx* c, double* algorithmic, double* executed) {
+    if (!c || !algorithmic || !executed) return ZIGP_EINVAL;
+    double alg = 0.0, exe = 0.0;
+    const double n = (double)c->n_local;
+    for (int l = 0; l < 2; l++) {
+        const Latent& L = c->lat[l];
+        alg += 6.0 * (double)L.M * L.M * n;                                    // 6 M^2 per point per latent
+        const double tri_tiles = 0.5 * L.ntc * (L.ntc + 1) * (double)BMN * BMN;  // MACs per point of one block-triangular product
+        exe += 2.0 * 5.0 * tri_tiles * n;                                       // 4 triangular products + 1 symmetric rank update
+    }
+    *algorithmic = alg; *executed = exe;
+    return ZIGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+"""ctypes binding of libzigp.so (C ABI in include/zigp.h).  There is no fallback: if the CUDA library is missing or no
+B200 is visible, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libzigp.so")
+
+OUT_HEADER = 4
+MAX_D = 8
+
+_lib = None
+
+SYMBOLS = {
+    # name: (restype, argtypes)
+    "zigp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
+    "zigp_destroy": (C.c_int, [C.c_void_p]),
+    "zigp_last_error": (C.c_char_p, [C.c_void_p]),
+    "zigp_theta_len": (C.c_int64, [C.c_void_p]),
+    "zigp_set_data_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
+    "zigp_set_data_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
+    "zigp_elbo_grad_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_elbo_grad_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_accumulate_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_accum_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "zigp_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_prior_kl_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "zigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "zigp_launch_count": (C.c_int64, [C.c_void_p]),
+    "zigp_flop_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+
+class ZigpError(RuntimeError):
+    pass
+
+
+class NotPositiveDefiniteError(ZigpError):
+    """Kmm + jitter*I is not positive definite (the reference surfaces this as a TF InvalidArgumentError)."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZigpError("libzigp.so not found at %s -- build it with `python __graft_entry__.py` (nvcc, sm_100a); "
+                            "there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(ctx, rc):
+    if rc == 0:
+        return
+    msg = lib().zigp_last_error(ctx)
+    msg = msg.decode() if msg else "zigp error %d" % rc
+    if rc == -4:
+        raise NotPositiveDefiniteError(msg)
+    raise ZigpError("%s (code %d)" % (msg, rc))
+
+
+class Context:
+    """Owns one zigp_ctx (one GPU)."""
+
+    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().zigp_create(C.byref(self._h), int(device), int(Mf), int(Mg), int(D), float(jitter), int(chunk_rows))
+        if rc != 0:
+            msg = lib().zigp_last_error(None)
+            raise ZigpError("%s (code %d)" % (msg.decode() if msg else "zigp_create failed", rc))
+        self.theta_len = int(lib().zigp_theta_len(self._h))
+        self.out_len = self.theta_len + OUT_HEADER
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().zigp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def call(self, name, *args):
+        check(self._h, getattr(lib(), name)(self._h, *args))
+
+    def accum_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self.call("zigp_accum_buffer", C.byref(p), C.byref(n))
+        return p.value, n.value
+
+    def debug_buffer(self, name: str, latent: int):
+        p, r, c, ld = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64()
+        self.call("zigp_debug_buffer", name.encode(), int(latent), C.byref(p), C.byref(r), C.byref(c), C.byref(ld))
+        return p.value, r.value, c.value, ld.value
+
+    def launch_count(self) -> int:
+        return int(lib().zigp_launch_count(self._h))
+
+    def flop_counts(self):
+        a, e = C.c_double(), C.c_double()
+        self.call("zigp_flop_counts", C.byref(a), C.byref(e))
+        return a.value, e.value
