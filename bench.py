@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- ELBO+grad points/sec of the OnOffSVGP objective (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                      (this repo's CUDA path)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               (CPU stand-in for the reference's TF1 path)
+
+Workload (config.workload): BASELINE.json configs[3] = synthetic 3-D spatio-temporal zero-inflated data, N = 2^24 points
+in total (fixed as GPUs are added -> strong scaling), M = 1024 inducing points per latent, RBF-ARD, float64.
+A step is one full ELBO + gradient evaluation: M-stage forward, the pass over all points (forward and backward), the
+all-reduce of the packed accumulator when N > 1, and the O(M^3) backward.  Prints ONE JSON line on rank 0."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "zero-inflated-gp_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "elbo_grad_points_per_sec"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 24, help="total points (default: the named config, 2^24)")
+    ap.add_argument("--m", type=int, default=1024)
+    ap.add_argument("--d", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 13, help="points per CPU-baseline evaluation")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm_load = sorted(sm)[len(sm) // 2] if sm else None
+        return {"sm_mhz": sm_load, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(N_sample, M, D, steps, warmup, threads=None):
+    """points/sec of the float64 CPU restatement (oracle/onoff_oracle.py: materialised Kmn, Cholesky, two triangular
+    solves per latent, autograd backward) on a bounded sample of the same workload."""
+    from onoffgpf import synth
+    from oracle import onoff_oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    X, Y = synth.make_data(N_sample, D, seed=0)
+    p = orc.as_params(**synth.make_params(M, M, D, seed=0))
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.elbo_and_grads(X, Y, p, num_data=N_sample)
+        ts.append(time.perf_counter() - t0)
+    ts = ts[warmup:]
+    dt = float(np.median(ts))
+    return N_sample / dt, dt, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, dt, threads = cpu_oracle_rate(a.cpu_sample, a.m, a.d, max(1, a.steps), max(1, a.warmup))
+    sample = "N_b=%d points of the same synthetic workload per step (Kmn is materialised, so the full N does not fit); float64" % a.cpu_sample
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic 3-D zero-inflated, N=2^24 total, M=%d per latent, RBF-ARD, fp64" % a.m if (a.n, a.d) == (1 << 24, 3) else "synthetic N=%d D=%d M=%d fp64" % (a.n, a.d, a.m),
+                       "N": a.n, "M": a.m, "D": a.d},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "note": "TF1/GPflow-0.4 cannot be installed here; this is the torch-float64 CPU port that follows the reference op for op"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def dgemm_peak(device):
+    """cuBLAS DGEMM TFLOP/s on this GPU, best of 5 (the fp64 roofline denominator; MEASURED_PEAKS.json has no fp64 entry)."""
+    n = 4096
+    a = torch.randn(n, n, device=device, dtype=torch.float64); b = torch.randn(n, n, device=device, dtype=torch.float64)
+    for _ in range(2):
+        torch.matmul(a, b)
+    torch.cuda.synchronize(device)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from onoffgpf import synth, _cabi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, M, D = a.n, a.m, a.d
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    n_loc = hi - lo
+
+    # synthetic data: generated per shard with a shard-specific seed (no rank needs the whole 2^24 x 3 array)
+    X, Y = synth.make_data(n_loc, D, seed=1000 + rank)
+    p = synth.make_params(M, M, D, seed=0)
+    Xh = torch.as_tensor(X).pin_memory(); Yh = torch.as_tensor(Y.reshape(-1)).pin_memory()
+    theta_h = torch.as_tensor(synth.pack_theta(p)).pin_memory()
+    m = synth.build_model(Xh.numpy(), Yh.numpy().reshape(-1, 1), p, device=dev, distributed=(world > 1), chunk_rows=(a.chunk or None))
+    ctx = m._ctx
+    theta = theta_h.to(dev)
+    out = torch.empty(ctx.out_len, dtype=torch.float64, device=dev)
+    out_h = torch.empty(ctx.out_len, dtype=torch.float64).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    ctx.call("zigp_set_data_dev", m._X_dev.data_ptr(), m._Y_dev.data_ptr(), n_loc, 1.0)
+
+    def step_resident():
+        ctx.call("zigp_accumulate_dev", theta.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            ptr, n = ctx.accum_buffer()
+            dist.all_reduce(m_wrap(ptr, n))
+        ctx.call("zigp_finish_dev", theta.data_ptr(), out.data_ptr(), stream.cuda_stream)
+
+    from onoffgpf.model import wrap_device_buffer
+    m_wrap = lambda ptr, n: wrap_device_buffer(ptr, n, dev)
+
+    def step_e2e():
+        # host buffers in, host result out: H2D of X, Y, theta and D2H of the packed result are inside the step
+        ctx.call("zigp_set_data_host", Xh.data_ptr(), Yh.data_ptr(), n_loc, 1.0, stream.cuda_stream)
+        theta.copy_(theta_h, non_blocking=True)
+        ctx.call("zigp_accumulate_dev", theta.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            ptr, n = ctx.accum_buffer()
+            dist.all_reduce(m_wrap(ptr, n))
+        ctx.call("zigp_finish_dev", theta.data_ptr(), out.data_ptr(), stream.cuda_stream)
+        out_h.copy_(out, non_blocking=True)
+        stream.synchronize()
+        return float(out_h[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    peak_tf = dgemm_peak(dev) if rank == 0 else 0.0
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms_total, _ = timed(step_resident, a.steps)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / a.steps
+    value = N / (ms_step * 1e-3)
+    # sanity: the result of the last step must be finite and the Cholesky must have succeeded
+    oh = out.cpu().numpy()
+    if not np.all(np.isfinite(oh)) or oh[3] != 0:
+        raise SystemExit("bench.py: non-finite result or Cholesky failure (info=%r)" % oh[3])
+
+    # end to end through host buffers
+    step_e2e()
+    ms_e2e_total, wall_e2e = timed(step_e2e, a.steps)
+    e2e_value = N / (max(ms_e2e_total, wall_e2e) / a.steps * 1e-3)
+    h2d = (n_loc * (D + 1) + ctx.theta_len) * 8 * world
+    d2h = ctx.out_len * 8 * world
+
+    # per-kernel-class device times of one profiled evaluation (outside the timed region)
+    ctx.set_profiling(True)
+    step_resident()
+    prof = ctx.profile_read()
+    ctx.set_profiling(False)
+    alg, exe = ctx.flop_counts()
+    gemm_ms, gemm_n = prof["gemm_tn"]
+    # dominant kernel: gemm_tn_f64<128,128,64,32,4>; one launch = one triangular product of a chunk of points with an
+    # M x M triangular factor: M^2 flop per point (each of the six products per latent is M^2 flop)
+    flops_per_launch = float(M) * M * (n_loc / max(1, gemm_n / 8))      # 8 launches per chunk (4 per latent)
+    achieved = flops_per_launch / (gemm_ms / max(1, gemm_n) * 1e-3) * 1e-12 if gemm_n else 0.0
+
+    if rank == 0:
+        cpu = None
+        if not a.no_cpu_baseline:
+            rate, dt, threads = cpu_oracle_rate(a.cpu_sample, M, D, steps=3, warmup=1)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "3 timed ELBO+grad evaluations of N_b=%d points (same generator, same M, D); median %.2f s each" % (a.cpu_sample, dt)}
+        total_prof = sum(v[0] for v in prof.values())
+        named = (N, M, D) == (1 << 24, 1024, 3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": ("BASELINE.json configs[3]: synthetic 3-D spatio-temporal zero-inflated, N=2^24 total, M=1024 per latent, RBF-ARD, fp64"
+                                    if named else "synthetic zero-inflated N=%d D=%d M=%d fp64 (dev override, not the named config)" % (N, D, M)),
+                       "N": N, "M": M, "D": D, "parallelism": "data-parallel over points, dp%d, one allreduce of %d doubles per step" % (world, ctx.accum_buffer()[1]),
+                       "l2": "inputs (X,Y %.0f MB) and per-chunk intermediates (%.0f MB) exceed the 126 MB L2; no explicit flush" % (n_loc * (D + 1) * 8 / 1e6, 64 * ctx_chunk_bytes(m) / 1e6),
+                       "elbo": float(oh[0])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "note": "zigp_set_data_host + accumulate/finish + D2H of the packed ELBO/gradient, pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_f64<128,128,64,32,4> (DMMA.8x8x4)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 4096^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue ceiling 37.1 TFLOP/s, profiles/microbench)",
+                         "whole_step_algorithmic_tflops": alg * world / (ms_step * 1e-3) * 1e-12 if world == 1 else None,
+                         "whole_step_frac": (alg / (ms_step * 1e-3) * 1e-12 / peak_tf) if (world == 1 and peak_tf) else None,
+                         "kernel_share_of_step": gemm_ms / total_prof if total_prof else None,
+                         "class_ms": {k: round(v[0], 3) for k, v in prof.items()}, "class_launches": {k: int(v[1]) for k, v in prof.items()}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctx_chunk_bytes(m):
+    # rows per chunk x padded M (one of the four chunk buffers per latent)
+    p, r, c, ld = m._ctx.debug_buffer("K", 0)
+    return r * ld
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

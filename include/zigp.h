@@ -88,6 +88,13 @@ int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xne
 int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t zigp_launch_count(const zigp_ctx* ctx);
+/* Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).  Classes:
+ * 0 kgen (Kmn tiles), 1 gemm_tn (the four triangular contractions), 2 point (likelihood), 3 kgrad (Kmn-side gradient sums),
+ * 4 syrk (E += A^T diag(gv) A), 5 M-stage forward, 6 M-stage backward, 7 slot reduction.  Off by default; switching it on or
+ * off clears the records.  zigp_profile_read synchronises the device. */
+#define ZIGP_PROFILE_CLASSES 8
+int zigp_set_profiling(zigp_ctx* ctx, int on);
+int zigp_profile_read(zigp_ctx* ctx, double* ms_by_class, int64_t* launches_by_class, int n_classes);
 /* algorithmic flop count of one ELBO+grad evaluation of the current data shard (12 M^2 per point per SURVEY 8(d)) and
  * the flops the kernels actually execute (block-triangular tiles, 10 M^2 formulation) */
 int zigp_flop_counts(const zigp_ctx* ctx, double* algorithmic, double* executed);

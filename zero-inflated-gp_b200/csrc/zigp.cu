@@ -59,6 +59,10 @@ struct zigp_ctx {
     std::vector<void*> allocs;
     std::string err;
     long long launches = 0;
+    // optional per-kernel-class timing (CUDA events on the launching stream; off by default)
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t a, b; int cat; };
+    std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -82,6 +86,18 @@ namespace {
 
 inline long long rup(long long x, long long a) { return (x + a - 1) / a * a; }
 
+enum ProfCat { PC_KGEN = 0, PC_GEMM = 1, PC_POINT = 2, PC_KGRAD = 3, PC_SYRK = 4, PC_MFWD = 5, PC_MBWD = 6, PC_REDUCE = 7, PC_COUNT = 8 };
+
+struct ProfScope {
+    zigp_ctx* c; cudaStream_t st; bool on; cudaEvent_t a{}, b{}; int cat;
+    ProfScope(zigp_ctx* c_, int cat_, cudaStream_t st_) : c(c_), st(st_), on(c_->profiling), cat(cat_) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(b, st); c->prof.push_back({a, b, cat}); }
+    }
+};
+
 int dalloc(zigp_ctx* c, double** p, long long n) {
     void* q = nullptr;
     CK(cudaMalloc(&q, (size_t)std::max<long long>(n, 1) * sizeof(double)));
@@ -99,6 +115,7 @@ int dalloc(zigp_ctx* c, double** p, long long n) {
 using GemmN = TnCfg<BMN, BMN, 64, 32, 4>;
 
 int gemmN(zigp_ctx* c, const GemmArgs& g, cudaStream_t st) {
+    ProfScope ps(c, PC_GEMM, st);
     CK((launch_gemm_tn<BMN, BMN, 64, 32, 4>(g, st)));
     c->launches++;
     return 0;
@@ -121,6 +138,7 @@ int gemmM(zigp_ctx* c, const double* In, long long ldi, const double* W, long lo
 
 // ---------------------------------------------------------------------------------------------------------------
 int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
+    ProfScope ps(c, PC_MFWD, st);
     Latent& L = c->lat[l];
     const int M = L.M, Mp = L.Mp, D = c->D;
     const long long MM = (long long)Mp * Mp;
@@ -183,8 +201,11 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
     Latent& L = c->lat[l];
     const int Mp = L.Mp;
     dim3 gk(Mp / 32, rows / 64);
-    kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb);
-    LAUNCHED();
+    {
+        ProfScope ps(c, PC_KGEN, st);
+        kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb);
+        LAUNCHED();
+    }
     GemmArgs g{};
     g.rows = rows; g.cols = Mp; g.kdim = Mp; g.alpha = 1.0; g.beta = 0.0;
     // A[n,m] = sum_{k<=m} K[n,k] T[m,k]           (onofftf/main.py:270, A = Lm^-1 Kmn)
@@ -216,6 +237,7 @@ int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long lon
     }
     p.noise = theta + 2 * c->D + 2;
     p.Y = Y; p.n0 = n0; p.nvalid = Y ? nvalid : 0; p.rows = rows; p.scale = c->scale; p.partial = c->pt_partial;
+    ProfScope ps(c, PC_POINT, st);
     point_kernel<<<rows / 256, 256, 0, st>>>(p);
     LAUNCHED();
     return 0;
@@ -244,16 +266,23 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
             k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
             dim3 gg(L.Mp / 128, (nvalid + KG_ROWS - 1) / KG_ROWS);
-            kgrad_kernel<<<gg, 128, 0, st>>>(k);
-            LAUNCHED();
+            {
+                ProfScope ps(c, PC_KGRAD, st);
+                kgrad_kernel<<<gg, 128, 0, st>>>(k);
+                LAUNCHED();
+            }
             SyrkArgs s{};
             s.A = L.Ab; s.lda = L.Mp; s.w = L.gv; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
             s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
-            CK((launch_syrk_nt<BMN, 64, 32, 3>(s, st)));
-            c->launches++;
+            {
+                ProfScope ps(c, PC_SYRK, st);
+                CK((launch_syrk_nt<BMN, 64, 32, 3>(s, st)));
+                c->launches++;
+            }
         }
     }
     // fold the per-CTA slots into the packed accumulator (fixed order -> deterministic)
+    ProfScope psr(c, PC_REDUCE, st);
     reduce_slots_kernel<<<1, 32, 0, st>>>(c->pt_partial, 4, c->pt_slots, c->accum, 4);
     LAUNCHED();
     for (int l = 0; l < 2; l++) {
@@ -320,6 +349,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs f) {
 
 int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
     CK(cudaSetDevice(c->device));
+    ProfScope ps(c, PC_MBWD, st);
     const int D = c->D;
     FinalArgs f{};
     f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.D = D;
@@ -612,6 +642,29 @@ int zigp_debug_buffer(zigp_ctx* c, const char* name, int latent, double** ptr, i
         if (n == e.nm) { *ptr = e.p; *rows = e.r; *cols = e.cdim; *ld = e.ldim; return ZIGP_OK; }
     c->err = "zigp_debug_buffer: unknown buffer name";
     return ZIGP_EINVAL;
+}
+
+int zigp_set_profiling(zigp_ctx* c, int on) {
+    if (!c) return ZIGP_EINVAL;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->prof.clear();
+    c->profiling = (on != 0);
+    return ZIGP_OK;
+}
+
+int zigp_profile_read(zigp_ctx* c, double* ms_by_class, int64_t* launches_by_class, int n_classes) {
+    if (!c || !ms_by_class || !launches_by_class || n_classes < PC_COUNT) return ZIGP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < n_classes; i++) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+    for (auto& r : c->prof) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_by_class[r.cat] += ms; launches_by_class[r.cat]++;
+    }
+    return ZIGP_OK;
 }
 
 int zigp_flop_counts(const zigp_ctx* c, double* algorithmic, double* executed) {

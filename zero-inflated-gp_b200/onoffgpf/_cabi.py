@@ -31,6 +31,8 @@ SYMBOLS = {
     "zigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "zigp_launch_count": (C.c_int64, [C.c_void_p]),
+    "zigp_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "zigp_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "zigp_flop_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
@@ -102,6 +104,17 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().zigp_launch_count(self._h))
+
+    PROFILE_CLASSES = ("kgen", "gemm_tn", "point", "kgrad", "syrk", "mstage_fwd", "mstage_bwd", "reduce")
+
+    def set_profiling(self, on: bool):
+        self.call("zigp_set_profiling", int(bool(on)))
+
+    def profile_read(self):
+        n = len(self.PROFILE_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        self.call("zigp_profile_read", ms, cnt, n)
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.PROFILE_CLASSES)}
 
     def flop_counts(self):
         a, e = C.c_double(), C.c_double()
