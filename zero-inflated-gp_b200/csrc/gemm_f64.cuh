@@ -16,7 +16,10 @@
 
 namespace zigp {
 
-constexpr int KT = 16;          // k-slab depth (doubles) staged per pipeline stage
+#ifndef ZIGP_KT
+#define ZIGP_KT 32
+#endif
+constexpr int KT = ZIGP_KT;     // k-slab depth (doubles) staged per pipeline stage
 constexpr int SPAD = 4;         // row padding -> stride 20 doubles == 4 (mod 16): DMMA fragment loads hit 32 distinct banks
 constexpr int SSTR = KT + SPAD;
 
@@ -54,7 +57,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // Fragment mapping (PTX m8n8k4): a = In_s[r0 + lane/4][k + lane%4], b = W_s[c0 + lane/4][k + lane%4],
 // c{0,1} = C[r0 + lane/4][c0 + 2*(lane%4) + {0,1}].
 // -------------------------------------------------------------------------------------------------------------------
-template <int BM, int BN, int WM, int WN, int STAGES>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB = 1>
 struct TnCfg {
     static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
     static constexpr int THREADS = WARPS_M * WARPS_N * 32;
@@ -62,10 +65,10 @@ struct TnCfg {
     static constexpr size_t SMEM = (size_t)STAGES * (BM + BN) * SSTR * sizeof(double);
 };
 
-template <int BM, int BN, int WM, int WN, int STAGES>
-__global__ void __launch_bounds__(TnCfg<BM, BN, WM, WN, STAGES>::THREADS, 1)
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB = 1>
+__global__ void __launch_bounds__(TnCfg<BM, BN, WM, WN, STAGES, MINB>::THREADS, MINB)
 gemm_tn_f64(const GemmArgs g) {
-    using C = TnCfg<BM, BN, WM, WN, STAGES>;
+    using C = TnCfg<BM, BN, WM, WN, STAGES, MINB>;
     extern __shared__ __align__(16) double smem[];
     double* sIn = smem;
     double* sW = smem + (size_t)STAGES * BM * SSTR;
@@ -92,13 +95,13 @@ gemm_tn_f64(const GemmArgs g) {
     auto load_slab = [&](int stage, int k0) {
         double* dIn = sIn + (size_t)stage * BM * SSTR;
         double* dW = sW + (size_t)stage * BN * SSTR;
-        // 8 chunks of 16 B per row
-        for (int c = tid; c < BM * 8; c += C::THREADS) {
-            int r = c >> 3, q = c & 7;
+        constexpr int CPR = KT / 2;    // 16-byte chunks per row
+        for (int c = tid; c < BM * CPR; c += C::THREADS) {
+            int r = c / CPR, q = c % CPR;
             cp_async16(dIn + r * SSTR + q * 2, gIn + (long long)r * g.ldi + k0 + q * 2);
         }
-        for (int c = tid; c < BN * 8; c += C::THREADS) {
-            int r = c >> 3, q = c & 7;
+        for (int c = tid; c < BN * CPR; c += C::THREADS) {
+            int r = c / CPR, q = c % CPR;
             cp_async16(dW + r * SSTR + q * 2, gW + (long long)r * g.ldw + k0 + q * 2);
         }
     };
@@ -193,10 +196,10 @@ gemm_tn_f64(const GemmArgs g) {
     }
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB = 1>
 inline cudaError_t launch_gemm_tn(const GemmArgs& g, cudaStream_t st) {
-    using C = TnCfg<BM, BN, WM, WN, STAGES>;
-    auto kern = gemm_tn_f64<BM, BN, WM, WN, STAGES>;
+    using C = TnCfg<BM, BN, WM, WN, STAGES, MINB>;
+    auto kern = gemm_tn_f64<BM, BN, WM, WN, STAGES, MINB>;
     static bool attr_done = false;   // per-instantiation; contexts are created per device before first use
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -221,7 +224,7 @@ struct SyrkArgs {
     int n, m, nsplit;
 };
 
-template <int BT, int WM, int WN, int STAGES>
+template <int BT, int WM, int WN, int STAGES, int MINB = 1>
 struct NtCfg {
     static constexpr int WARPS_M = BT / WM, WARPS_N = BT / WN;
     static constexpr int THREADS = WARPS_M * WARPS_N * 32;
@@ -230,10 +233,10 @@ struct NtCfg {
     static constexpr size_t SMEM = (size_t)STAGES * (2 * KT * STR + KT) * sizeof(double);
 };
 
-template <int BT, int WM, int WN, int STAGES>
-__global__ void __launch_bounds__(NtCfg<BT, WM, WN, STAGES>::THREADS, 1)
+template <int BT, int WM, int WN, int STAGES, int MINB = 1>
+__global__ void __launch_bounds__(NtCfg<BT, WM, WN, STAGES, MINB>::THREADS, MINB)
 syrk_nt_f64(const SyrkArgs g) {
-    using C = NtCfg<BT, WM, WN, STAGES>;
+    using C = NtCfg<BT, WM, WN, STAGES, MINB>;
     extern __shared__ __align__(16) double smem[];
     constexpr int STAGE_D = 2 * KT * C::STR + KT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -318,10 +321,10 @@ syrk_nt_f64(const SyrkArgs g) {
     }
 }
 
-template <int BT, int WM, int WN, int STAGES>
+template <int BT, int WM, int WN, int STAGES, int MINB = 1>
 inline cudaError_t launch_syrk_nt(const SyrkArgs& g, cudaStream_t st) {
-    using C = NtCfg<BT, WM, WN, STAGES>;
-    auto kern = syrk_nt_f64<BT, WM, WN, STAGES>;
+    using C = NtCfg<BT, WM, WN, STAGES, MINB>;
+    auto kern = syrk_nt_f64<BT, WM, WN, STAGES, MINB>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);

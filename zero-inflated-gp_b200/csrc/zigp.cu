@@ -112,11 +112,47 @@ int dalloc(zigp_ctx* c, double** p, long long n) {
         if (r_) return r_;                            \
     } while (0)
 
-using GemmN = TnCfg<BMN, BMN, 64, 32, 4>;
+#ifndef ZIGP_BM
+#define ZIGP_BM 64
+#endif
+#ifndef ZIGP_BN
+#define ZIGP_BN 64
+#endif
+#ifndef ZIGP_MINB
+#define ZIGP_MINB 3
+#endif
+// Tile configuration (profiles/tune_r01*.txt): the fp64 pipe issues one DMMA.8x8x4 per 16 cycles per SM sub-partition, so a
+// single warp per sub-partition can saturate it; what costs time is every cycle in which no warp of the SM is inside the
+// k-loop (barrier skew, tile prologue / epilogue).  Small 64x64 tiles with 3 resident CTAs per SM hide those phases of one
+// CTA behind the k-loops of the others: 0.72 -> 0.89 of the cuBLAS DGEMM rate against 128x128 tiles with one CTA per SM.
+#ifndef ZIGP_SBT
+#define ZIGP_SBT 64
+#endif
+#ifndef ZIGP_SWM
+#define ZIGP_SWM 32
+#endif
+#ifndef ZIGP_SWN
+#define ZIGP_SWN 32
+#endif
+#ifndef ZIGP_SSTAGES
+#define ZIGP_SSTAGES 2
+#endif
+#ifndef ZIGP_SMINB
+#define ZIGP_SMINB 3
+#endif
+#ifndef ZIGP_WM
+#define ZIGP_WM 32
+#endif
+#ifndef ZIGP_WN
+#define ZIGP_WN 32
+#endif
+#ifndef ZIGP_STAGES
+#define ZIGP_STAGES 2
+#endif
 
 int gemmN(zigp_ctx* c, const GemmArgs& g, cudaStream_t st) {
     ProfScope ps(c, PC_GEMM, st);
-    CK((launch_gemm_tn<BMN, BMN, 64, 32, 4>(g, st)));
+    CK((launch_gemm_tn<ZIGP_BM, ZIGP_BN, ZIGP_WM, ZIGP_WN, ZIGP_STAGES, ZIGP_MINB>(g, st)));
     c->launches++;
     return 0;
 }
@@ -276,7 +312,7 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
             {
                 ProfScope ps(c, PC_SYRK, st);
-                CK((launch_syrk_nt<BMN, 64, 32, 3>(s, st)));
+                CK((launch_syrk_nt<ZIGP_SBT, ZIGP_SWM, ZIGP_SWN, ZIGP_SSTAGES, ZIGP_SMINB>(s, st)));
                 c->launches++;
             }
         }
@@ -388,12 +424,6 @@ __global__ void kl_out_kernel(const double* klf, const double* klg, const int* i
     out[1] = (double)info[0];
 }
 
-int ensure_chunk_buffers(zigp_ctx* c) {
-    // N-stage buffers are sized for c->chunk rows at creation; nothing to do (kept for symmetry / future resizing)
-    (void)c;
-    return 0;
-}
-
 }  // namespace
 
 // =================================================================================================================
@@ -438,7 +468,7 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
     long long acc_len = 4;
     for (int l = 0; l < 2; l++) {
         Latent& L = c->lat[l];
-        L.Mp = (int)rup(L.M, BMN); L.nb = L.Mp / NB; L.ntc = L.Mp / BMN;
+        L.Mp = (int)rup(L.M, BMN); L.nb = L.Mp / NB; L.ntc = L.Mp / ZIGP_BN;
         acc_len += (long long)L.Mp * L.Mp + (long long)(2 + 2 * D) * L.Mp;
     }
     c->accum_len = acc_len;
@@ -471,9 +501,9 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
             DA(L.mean, chunk); DA(L.vr, chunk); DA(L.gm, chunk); DA(L.gv, chunk);
             DA(L.kg_partial, (long long)c->kg_slots * (2 + 2 * D) * Mp);
             // SYRK split count: fill the 148 SMs with (lower tiles) x (splits); each split a multiple of 16 rows of a 512-multiple
-            const int tiles = L.ntc * (L.ntc + 1) / 2;
+            const int nts = L.Mp / ZIGP_SBT, tiles = nts * (nts + 1) / 2;
             int ns = 1;
-            while (ns < 32 && tiles * ns < 148) ns *= 2;
+            while (ns < 512 / KT && tiles * ns < 148 * ZIGP_SMINB) ns *= 2;   // every split stays a multiple of KT rows
             L.nsplit = ns;
             DA(L.E_splits, (long long)ns * MM);
         }
@@ -674,8 +704,10 @@ int zigp_flop_counts(const zigp_ctx* c, double* algorithmic, double* executed) {
     for (int l = 0; l < 2; l++) {
         const Latent& L = c->lat[l];
         alg += 6.0 * (double)L.M * L.M * n;                                    // 6 M^2 per point per latent
-        const double tri_tiles = 0.5 * L.ntc * (L.ntc + 1) * (double)BMN * BMN;  // MACs per point of one block-triangular product
-        exe += 2.0 * 5.0 * tri_tiles * n;                                       // 4 triangular products + 1 symmetric rank update
+        const double tri_tiles = 0.5 * L.ntc * (L.ntc + 1) * (double)ZIGP_BN * ZIGP_BN;  // MACs per point of one block-triangular product
+        const int nts = L.Mp / ZIGP_SBT;
+        const double syrk_tiles = 0.5 * nts * (nts + 1) * (double)ZIGP_SBT * ZIGP_SBT;
+        exe += 2.0 * (4.0 * tri_tiles + syrk_tiles) * n;                        // 4 triangular products + 1 symmetric rank update
     }
     *algorithmic = alg; *executed = exe;
     return ZIGP_OK;

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libzigp.so")
+LIB_PATH = os.environ.get("ZIGP_LIB") or os.path.join(os.path.dirname(_HERE), "libzigp.so")   # ZIGP_LIB: tuning variants
 
 OUT_HEADER = 4
 MAX_D = 8

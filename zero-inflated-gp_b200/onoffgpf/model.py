@@ -301,7 +301,8 @@ class OnOffSVGP(Parameterized):
             return f, g
 
         x0 = self.get_free_state()
-        opts = dict(maxiter=maxiter, disp=kw.pop("disp", False))
+        kw.pop("disp", None)
+        opts = dict(maxiter=maxiter)
         opts.update(kw)
         res = minimize(fun, x0, jac=True, method=method, tol=tol, callback=callback, options=opts)
         self.set_state(res.x)
