@@ -36,9 +36,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 24, help="total points (default: the named config, 2^24)")
-    ap.add_argument("--m", type=int, default=1024)
-    ap.add_argument("--d", type=int, default=3)
+    ap.add_argument("--points", dest="n", type=int, default=1 << 24, help="total points (default: the named config, 2^24)")
+    ap.add_argument("--inducing", dest="m", type=int, default=1024)
+    ap.add_argument("--dims", dest="d", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1 << 13, help="points per CPU-baseline evaluation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0)
@@ -155,7 +155,8 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N, M, D = a.n, a.m, a.d
-    lo, hi = rank * N // world, (rank + 1) * N // world
+    from onoffgpf.parallel import shard_bounds
+    lo, hi = shard_bounds(N, rank, world)
     n_loc = hi - lo
 
     # synthetic data: generated per shard with a shard-specific seed (no rank needs the whole 2^24 x 3 array)

@@ -72,19 +72,23 @@ def latent_fwd(X, Z, ell, var, ms):
     return K, A, RA, mean, v, V, Y
 
 
-def latent_bwd(X, Z, ell, var, mu, s, jitter, ms, K, A, Y, gm, gv):
-    """returns grads (Z, ell, var, mu, s) of [data term], plus -KL contributions, from the sufficient statistics."""
-    M, D = Z.shape
-    T, aw, beta, Rt = ms["T"], ms["aw"], ms["beta"], ms["Rt"]
+def latent_stats(X, Z, ell, ms, K, A, Y, gm, gv):
+    """per-shard sufficient statistics (what one rank accumulates; they add across shards)"""
     E = (A * gv[:, None]).T @ A
     a = A.T @ gm
-    # Kmn side
-    G = (gm[:, None] * beta[None, :] - 2 * gv[:, None] * Y) * K      # N x M
-    diff = X[:, None, :] - Z[None, :, :]                             # N x M x D
-    gZ = (G[:, :, None] * diff).sum(0) / (ell * ell)
-    gell = (G[:, :, None] * diff * diff).sum((0, 1)) / ell ** 3
-    gvar = G.sum() / var + gv.sum()
-    # Kmm side (includes -KL)
+    G = (gm[:, None] * ms["beta"][None, :] - 2 * gv[:, None] * Y) * K      # N x M
+    diff = X[:, None, :] - Z[None, :, :]                                   # N x M x D
+    return dict(E=E, a=a, S0=G.sum(0), S1=(G[:, :, None] * diff).sum(0), Q=(G[:, :, None] * diff * diff).sum(0), sgv=gv.sum())
+
+
+def latent_finish(st, Z, ell, var, mu, s, jitter, ms):
+    """O(M^3) backward from the (all-reduced) statistics; includes the -KL terms, so it must run exactly once per rank"""
+    M, D = Z.shape
+    T, aw, Rt = ms["T"], ms["aw"], ms["Rt"]
+    E, a = st["E"], st["a"]
+    gZ = st["S1"] / (ell * ell)
+    gell = st["Q"].sum(0) / ell ** 3
+    gvar = st["S0"].sum() / var + st["sgv"]
     P = Rt @ Rt.T
     EP = E @ P
     I = torch.eye(M, dtype=DT)
@@ -102,25 +106,66 @@ def latent_bwd(X, Z, ell, var, mu, s, jitter, ms, K, A, Y, gm, gv):
     return gZ, gell, gvar, gmu, gs
 
 
-def elbo_and_grads(X, Y, p, num_data=None, jitter=1e-6):
-    X = torch.as_tensor(X, dtype=DT); y = torch.as_tensor(Y, dtype=DT).reshape(-1)
-    N = X.shape[0]
-    scale = (num_data or N) / N
+def _split(p):
     f = dict(Z=p["Zf"], ell=p["kernf_lengthscales"].reshape(-1), var=p["kernf_variance"].reshape(()), mu=p["u_fm"].reshape(-1), s=p["u_fs_sqrt"].reshape(-1))
     g = dict(Z=p["Zg"], ell=p["kerng_lengthscales"].reshape(-1), var=p["kerng_variance"].reshape(()), mu=p["u_gm"].reshape(-1), s=p["u_gs_sqrt"].reshape(-1))
+    return f, g
+
+
+def accumulate(X, Y, p, scale, jitter=1e-6):
+    """one rank's pass over its shard -> additive statistics (mirrors zigp_accumulate_dev)"""
+    X = torch.as_tensor(X, dtype=DT); y = torch.as_tensor(Y, dtype=DT).reshape(-1)
+    f, g = _split(p)
     noise = p["likelihood_variance"].reshape(())
-    out = {}
     st = {}
     for nm, q in (("f", f), ("g", g)):
         ms = mstage_fwd(q["Z"], q["ell"], q["var"], q["mu"], q["s"], jitter)
         st[nm] = (ms,) + latent_fwd(X, q["Z"], q["ell"], q["var"], ms)
     ll, gmf, gvf, gmg, gvg, gnoise = point_stage(st["f"][4], st["f"][5], st["g"][4], st["g"][5], y, noise, scale)
-    data = ll.sum()
-    KL = st["f"][0]["KL"] + st["g"][0]["KL"]
-    grads = {"likelihood_variance": gnoise}
+    out = {"ll": ll.sum(), "dnoise": gnoise}
     for nm, q, gm, gv in (("f", f, gmf, gvf), ("g", g, gmg, gvg)):
         ms, K, A, RA, mean, v, V, Yy = st[nm]
-        gZ, gell, gvar, gmu, gs = latent_bwd(X, q["Z"], q["ell"], q["var"], q["mu"], q["s"], jitter, ms, K, A, Yy, gm, gv)
+        out[nm] = latent_stats(X, q["Z"], q["ell"], ms, K, A, Yy, gm, gv)
+    return out
+
+
+STAT_KEYS = ("E", "a", "S0", "S1", "Q", "sgv")
+
+
+def pack_stats(st):
+    parts = [st["ll"].reshape(1), st["dnoise"].reshape(1)]
+    for nm in ("f", "g"):
+        parts += [st[nm][k].reshape(-1) for k in STAT_KEYS]
+    return torch.cat(parts)
+
+
+def unpack_stats(buf, like):
+    out = {"ll": buf[0], "dnoise": buf[1]}
+    o = 2
+    for nm in ("f", "g"):
+        out[nm] = {}
+        for k in STAT_KEYS:
+            n = like[nm][k].numel()
+            out[nm][k] = buf[o:o + n].reshape(like[nm][k].shape)
+            o += n
+    return out
+
+
+def finish(st, p, scale, jitter=1e-6):
+    """mirrors zigp_finish_dev: every rank runs this on the reduced statistics"""
+    f, g = _split(p)
+    grads = {"likelihood_variance": st["dnoise"]}
+    KL = 0.0
+    for nm, q in (("f", f), ("g", g)):
+        ms = mstage_fwd(q["Z"], q["ell"], q["var"], q["mu"], q["s"], jitter)
+        KL = KL + ms["KL"]
+        gZ, gell, gvar, gmu, gs = latent_finish(st[nm], q["Z"], q["ell"], q["var"], q["mu"], q["s"], jitter, ms)
         grads["Z" + nm] = gZ; grads["kern%s_lengthscales" % nm] = gell; grads["kern%s_variance" % nm] = gvar
         grads["u_%sm" % nm] = gmu.reshape(-1, 1); grads["u_%ss_sqrt" % nm] = gs.reshape(-1, 1)
-    return float(data * scale - KL), float(data), float(KL), grads
+    return float(st["ll"] * scale - KL), float(st["ll"]), float(KL), grads
+
+
+def elbo_and_grads(X, Y, p, num_data=None, jitter=1e-6):
+    N = len(X)
+    scale = (num_data or N) / N
+    return finish(accumulate(X, Y, p, scale, jitter), p, scale, jitter)

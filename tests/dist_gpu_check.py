@@ -1,0 +1,42 @@
+"""Launched by torchrun (one rank per GPU): every rank gives OnOffSVGP its own shard; the all-reduced result must equal the
+oracle on the full data set and be identical on all ranks.  Prints DIST_OK on rank 0."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "zero-inflated-gp_b200"), ROOT):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from onoffgpf import synth
+from onoffgpf.parallel import shard_bounds
+from oracle import onoff_oracle as orc
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+N, M, D = 6001, 130, 3
+X, Y = synth.make_data(N, D, 17)
+p = synth.make_params(M, M, D, 17)
+lo, hi = shard_bounds(N, rank, world)
+m = synth.build_model(X[lo:hi], Y[lo:hi], p, device=dev, distributed=True, chunk_rows=1024)
+assert m.num_data == N
+elbo = m.build_likelihood()
+grads = torch.autograd.grad(elbo, m.trainable_tensors())
+flat = torch.cat([elbo.reshape(1)] + [g.reshape(-1) for g in grads])
+gathered = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(gathered, flat)
+for g in gathered[1:]:
+    assert torch.equal(g, gathered[0]), "ranks disagree"
+if rank == 0:
+    e, _, _, gf = orc.elbo_and_grads(X, Y, orc.as_params(**p), free=True)
+    assert abs(float(elbo) - e) <= 1e-10 * abs(e), (float(elbo), e)
+    full = np.sqrt(sum(float((v ** 2).sum()) for v in gf.values()))
+    for k, g in zip(orc.PARAM_NAMES, grads):
+        a, b = g.cpu().numpy().reshape(-1), gf[k].numpy().reshape(-1)
+        assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(b) + 1e-12 * full, k
+    print("DIST_OK world=%d elbo=%.12e" % (world, float(elbo)), flush=True)
+dist.destroy_process_group()

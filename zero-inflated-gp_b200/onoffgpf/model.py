@@ -18,12 +18,12 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, parallel
 from .likelihood import OnOffLikelihood
 from .param import DTYPE, DataHolder, Param, Parameterized, positive
 
 JITTER_LEVEL = 1e-6          # gpflow 0.4 settings.numerics.jitter_level (onoffgpf/OnOffSVGP.py:96-97)
-DEFAULT_CHUNK_ROWS = 32768
+DEFAULT_CHUNK_ROWS = 65536
 
 
 class _DevBuf:
@@ -115,12 +115,7 @@ class OnOffSVGP(Parameterized):
         self.distributed = bool(distributed) and torch.distributed.is_available() and torch.distributed.is_initialized()
         n_local = X.shape[0]
         self.num_data_local = n_local
-        if self.distributed:
-            t = torch.tensor([n_local], dtype=torch.int64, device=self.device)
-            torch.distributed.all_reduce(t)
-            self.num_data = int(t.item())
-        else:
-            self.num_data = n_local
+        self.num_data = parallel.global_count(n_local, self.device) if self.distributed else n_local
         if minibatch_size is None:
             minibatch_size = n_local
         self.minibatch_size = int(minibatch_size)
@@ -178,12 +173,7 @@ class OnOffSVGP(Parameterized):
             it = torch.as_tensor(idx, device=self.device)
             self._Xb, self._Yb = self._X_dev[it].contiguous(), self._Y_dev[it].contiguous()
         n_b = self._Xb.shape[0]
-        if self.distributed:
-            t = torch.tensor([n_b], dtype=torch.int64, device=self.device)
-            torch.distributed.all_reduce(t)
-            n_global = int(t.item())
-        else:
-            n_global = n_b
+        n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
         scale = float(self.num_data) / float(n_global)        # onoffgpf/OnOffSVGP.py:119-120
         self._ctx.call("zigp_set_data_dev", self._Xb.data_ptr(), self._Yb.data_ptr(), n_b, scale)
 
@@ -194,11 +184,19 @@ class OnOffSVGP(Parameterized):
             self._next_batch()
             out = torch.empty(self._ctx.out_len, dtype=DTYPE, device=self.device)
             st = self._stream()
-            self._ctx.call("zigp_accumulate_dev", theta.data_ptr(), st)
-            if self.distributed:
+
+            def accumulate():
+                self._ctx.call("zigp_accumulate_dev", theta.data_ptr(), st)
                 ptr, n = self._ctx.accum_buffer()
-                torch.distributed.all_reduce(wrap_device_buffer(ptr, n, self.device))
-            self._ctx.call("zigp_finish_dev", theta.data_ptr(), out.data_ptr(), st)
+                return wrap_device_buffer(ptr, n, self.device)
+
+            def finish(_reduced):
+                self._ctx.call("zigp_finish_dev", theta.data_ptr(), out.data_ptr(), st)
+
+            if self.distributed:
+                parallel.evaluate_sharded(accumulate, finish)
+            else:
+                finish(accumulate())
             info = int(out[3].item())
             if info != 0:
                 k = info - 1
