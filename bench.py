@@ -247,7 +247,7 @@ def run_ours(a):
     ctx.set_profiling(False)
     alg, exe = ctx.flop_counts()
     gemm_ms, gemm_n = prof["gemm_tn"]
-    # dominant kernel: gemm_tn_f64<128,128,64,32,4>; one launch = one triangular product of a chunk of points with an
+    # dominant kernel: gemm_tn_f64<64,64,32,32,2,3>; one launch = one triangular product of a chunk of points with an
     # M x M triangular factor: M^2 flop per point (each of the six products per latent is M^2 flop)
     flops_per_launch = float(M) * M * (n_loc / max(1, gemm_n / 8))      # 8 launches per chunk (4 per latent)
     achieved = flops_per_launch / (gemm_ms / max(1, gemm_n) * 1e-3) * 1e-12 if gemm_n else 0.0
@@ -272,7 +272,7 @@ def run_ours(a):
                     "note": "zigp_set_data_host + accumulate/finish + D2H of the packed ELBO/gradient, pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_f64<128,128,64,32,4> (DMMA.8x8x4)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue ceiling 37.1 TFLOP/s, profiles/microbench)",
                          "whole_step_algorithmic_tflops": alg * world / (ms_step * 1e-3) * 1e-12 if world == 1 else None,

@@ -129,17 +129,43 @@ gemm_tn_f64(const GemmArgs g) {
         }
         const double* cIn = sIn + (size_t)(it % STAGES) * BM * SSTR + (wm * WM + fr) * SSTR + fk;
         const double* cW = sW + (size_t)(it % STAGES) * BN * SSTR + (wn * WN + fr) * SSTR + fk;
+        const int k0 = kbeg + it * KT;
+        const bool on_diag = (g.tri != TRI_FULL) && (k0 + KT > col0) && (k0 < col0 + BN);
+        if (!on_diag) {
 #pragma unroll
-        for (int kk = 0; kk < KT; kk += 4) {
-            double a[C::FM], b[C::FN];
+            for (int kk = 0; kk < KT; kk += 4) {
+                double a[C::FM], b[C::FN];
 #pragma unroll
-            for (int i = 0; i < C::FM; i++) a[i] = cIn[i * 8 * SSTR + kk];
+                for (int i = 0; i < C::FM; i++) a[i] = cIn[i * 8 * SSTR + kk];
 #pragma unroll
-            for (int j = 0; j < C::FN; j++) b[j] = cW[j * 8 * SSTR + kk];
+                for (int j = 0; j < C::FN; j++) b[j] = cW[j * 8 * SSTR + kk];
 #pragma unroll
-            for (int i = 0; i < C::FM; i++)
+                for (int i = 0; i < C::FM; i++)
 #pragma unroll
-                for (int j = 0; j < C::FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    for (int j = 0; j < C::FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        } else {
+            // slab crosses the diagonal block of the triangular factor: skip every 8-column x 4-k fragment of W that is
+            // identically zero (LOWER: k > c for all of it; UPPER: k < c), so the executed work follows the triangle at
+            // 8 x 4 granularity instead of at tile granularity
+            const int cw = col0 + wn * WN;
+#pragma unroll
+            for (int kk = 0; kk < KT; kk += 4) {
+                const int ks = k0 + kk;
+                double a[C::FM];
+#pragma unroll
+                for (int i = 0; i < C::FM; i++) a[i] = cIn[i * 8 * SSTR + kk];
+#pragma unroll
+                for (int j = 0; j < C::FN; j++) {
+                    const int jc = cw + 8 * j;
+                    const bool needed = (g.tri == TRI_LOWER) ? (ks <= jc + 7) : (ks + 3 >= jc);
+                    if (needed) {                       // warp-uniform
+                        const double b = cW[j * 8 * SSTR + kk];
+#pragma unroll
+                        for (int i = 0; i < C::FM; i++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
+                    }
+                }
+            }
         }
     }
     cp_async_wait<0>();
@@ -214,12 +240,13 @@ inline cudaError_t launch_gemm_tn(const GemmArgs& g, cudaStream_t st) {
 
 // -------------------------------------------------------------------------------------------------------------------
 // NT engine (weighted SYRK over the point dimension), lower tiles only, split over n.
-//   Ebuf[split][i,j] += sum_{n in split} w[n] A[n,i] A[n,j]       (ld = ldE, tiles with tj > ti are not touched)
+//   Ebuf[split][i,j] += sum_{n in split} Aw[n,i] A[n,j],  Aw = diag(w) A   (ld = ldE, tiles with tj > ti are not touched)
+// The row weights are applied once by the producer of Aw (kgrad_kernel): a DMUL in this loop shares the fp64 pipe with the
+// DMMAs and serialises the warp (profiles/ncu_syrk_r01_v1: 15 % of the stall samples sat on the DMULs).
 // smem stage: [KT n-rows][BT + 4] for the i-tile and the j-tile (stride 132 == 4 mod 16 -> conflict-free fragments).
 // -------------------------------------------------------------------------------------------------------------------
 struct SyrkArgs {
-    const double* A; long long lda;    // n x m
-    const double* w;                   // n weights
+    const double* Aw; const double* A; long long lda;    // n x m each: Aw = diag(w) A (row-scaled copy), A
     double* E; long long ldE; long long split_stride;   // [nsplit][m x m]
     int n, m, nsplit;
 };
@@ -230,7 +257,7 @@ struct NtCfg {
     static constexpr int THREADS = WARPS_M * WARPS_N * 32;
     static constexpr int FM = WM / 8, FN = WN / 8;
     static constexpr int STR = BT + 4;
-    static constexpr size_t SMEM = (size_t)STAGES * (2 * KT * STR + KT) * sizeof(double);
+    static constexpr size_t SMEM = (size_t)STAGES * (2 * KT * STR) * sizeof(double);
 };
 
 template <int BT, int WM, int WN, int STAGES, int MINB = 1>
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(NtCfg<BT, WM, WN, STAGES, MINB>::THREADS, MINB
 syrk_nt_f64(const SyrkArgs g) {
     using C = NtCfg<BT, WM, WN, STAGES, MINB>;
     extern __shared__ __align__(16) double smem[];
-    constexpr int STAGE_D = 2 * KT * C::STR + KT;
+    constexpr int STAGE_D = 2 * KT * C::STR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % C::WARPS_M, wn = warp / C::WARPS_M;
 
@@ -249,23 +276,22 @@ syrk_nt_f64(const SyrkArgs g) {
     while (ti * (ti + 1) / 2 > t) ti--;
     const int tj = t - ti * (ti + 1) / 2;
     const int split = blockIdx.y;
-    const int nper = g.n / g.nsplit;            // multiple of KT by construction
-    const int n0 = split * nper;
-    const int nslab = nper / KT;
+    // the n/KT slabs are dealt to the splits as evenly as integers allow
+    const long long S = g.n / KT;
+    const int slab_lo = (int)(S * split / g.nsplit), slab_hi = (int)(S * (split + 1) / g.nsplit);
+    const int n0 = slab_lo * KT;
+    const int nslab = slab_hi - slab_lo;
     const int i0 = ti * BT, j0 = tj * BT;
 
     auto load_slab = [&](int stage, int nn) {
         double* dI = smem + (size_t)stage * STAGE_D;
         double* dJ = dI + KT * C::STR;
-        double* dWt = dJ + KT * C::STR;
         constexpr int CH = BT / 2;              // 16-byte chunks per row
         for (int c = tid; c < KT * CH; c += C::THREADS) {
             int r = c / CH, q = c % CH;
-            const double* src = g.A + (long long)(nn + r) * g.lda;
-            cp_async16(dI + r * C::STR + q * 2, src + i0 + q * 2);
-            cp_async16(dJ + r * C::STR + q * 2, src + j0 + q * 2);
+            cp_async16(dI + r * C::STR + q * 2, g.Aw + (long long)(nn + r) * g.lda + i0 + q * 2);
+            cp_async16(dJ + r * C::STR + q * 2, g.A + (long long)(nn + r) * g.lda + j0 + q * 2);
         }
-        if (tid < KT / 2) cp_async16(dWt + tid * 2, g.w + nn + tid * 2);
     };
 
     double acc[C::FM][C::FN][2];
@@ -290,13 +316,11 @@ syrk_nt_f64(const SyrkArgs g) {
         }
         const double* sI = smem + (size_t)(it % STAGES) * STAGE_D;
         const double* sJ = sI + KT * C::STR;
-        const double* sWt = sJ + KT * C::STR;
 #pragma unroll
         for (int kk = 0; kk < KT; kk += 4) {
-            const double wk = sWt[kk + fk];
             double a[C::FM], b[C::FN];
 #pragma unroll
-            for (int i = 0; i < C::FM; i++) a[i] = sI[(kk + fk) * C::STR + wm * WM + i * 8 + fr] * wk;
+            for (int i = 0; i < C::FM; i++) a[i] = sI[(kk + fk) * C::STR + wm * WM + i * 8 + fr];
 #pragma unroll
             for (int j = 0; j < C::FN; j++) b[j] = sJ[(kk + fk) * C::STR + wn * WN + j * 8 + fr];
 #pragma unroll

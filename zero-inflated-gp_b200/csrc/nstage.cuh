@@ -148,16 +148,17 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 // Kmn-side kernel gradient sums.  With  kbar[n,m] = gm_n * beta_m - 2 gv_n * Y[n,m]  and  G = kbar * K :
 //   S0[m]   += sum_n G              S1[d][m] += sum_n G (x_nd - z_md)        Q[d][m] += sum_n G (x_nd - z_md)^2
-//   a[m]    += sum_n gm_n A[n,m]
+//   a[m]    += sum_n gm_n A[n,m]                 and writes Aw[n,m] = gv_n A[n,m] for the symmetric rank update
 // Block = 128 columns x KG_ROWS rows; partial sums land in slot [blockIdx.y] (owned by this CTA across chunks).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int KG_ROWS = 256;
 struct KgradArgs {
     const double* K; const double* Y; const double* A; long long ld;
     const double* gm; const double* gv; const double* beta;
-    const double* X; long long n0; int nvalid;
+    const double* X; long long n0; int nvalid, rows;
     const double* Z; int M, D, Mp;
     double* partial;     // [nslots][2 + 2*D][Mp]
+    double* Aw;          // out: gv[n] * A[n,m]  (row-scaled copy consumed by syrk_nt_f64), same ld
 };
 
 __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
@@ -166,7 +167,11 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
     const int m = blockIdx.x * 128 + threadIdx.x;
     const int r0 = blockIdx.y * KG_ROWS;
     const int nr = min(KG_ROWS, p.nvalid - r0);
-    if (nr <= 0) return;
+    if (nr <= 0) {                                     // padding rows of the chunk: Aw must still be defined (zero)
+        const int nz = min(KG_ROWS, p.rows - r0);
+        for (int r = 0; r < nz; r++) p.Aw[(long long)(r0 + r) * p.ld + m] = 0.0;
+        return;
+    }
     for (int e = threadIdx.x; e < nr * p.D; e += 128) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
     for (int e = threadIdx.x; e < nr; e += 128) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
     __syncthreads();
@@ -178,9 +183,11 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
     const double* Kp = p.K + (long long)r0 * p.ld + m;
     const double* Yp = p.Y + (long long)r0 * p.ld + m;
     const double* Ap = p.A + (long long)r0 * p.ld + m;
-#pragma unroll 4
+    double* Awp = p.Aw + (long long)r0 * p.ld + m;
+#pragma unroll 8
     for (int r = 0; r < nr; r++) {
         const double k = Kp[(long long)r * p.ld], yy = Yp[(long long)r * p.ld], aa = Ap[(long long)r * p.ld];
+        Awp[(long long)r * p.ld] = sgv[r] * aa;
         const double G = (sgm[r] * bm - 2.0 * sgv[r] * yy) * k;
         s0 += G;
         am = fma(sgm[r], aa, am);
@@ -189,6 +196,7 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
             if (d < p.D) { double df = sx[r][d] - z[d]; s1[d] = fma(G, df, s1[d]); q[d] = fma(G * df, df, q[d]); }
         }
     }
+    for (int r = nr; r < min(KG_ROWS, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
     double* out = p.partial + (long long)blockIdx.y * (2 + 2 * p.D) * p.Mp + m;
     out[0] += s0;
     out[(long long)p.Mp] += am;

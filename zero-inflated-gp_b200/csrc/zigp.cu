@@ -300,15 +300,15 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             Latent& L = c->lat[l];
             KgradArgs k{};
             k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
-            k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
-            dim3 gg(L.Mp / 128, (nvalid + KG_ROWS - 1) / KG_ROWS);
+            k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows; k.Aw = L.Vb; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
+            dim3 gg(L.Mp / 128, (rows + KG_ROWS - 1) / KG_ROWS);
             {
                 ProfScope ps(c, PC_KGRAD, st);
                 kgrad_kernel<<<gg, 128, 0, st>>>(k);
                 LAUNCHED();
             }
             SyrkArgs s{};
-            s.A = L.Ab; s.lda = L.Mp; s.w = L.gv; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
+            s.Aw = L.Vb; s.A = L.Ab; s.lda = L.Mp; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
             s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
             {
                 ProfScope ps(c, PC_SYRK, st);
@@ -500,10 +500,16 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
             DA(L.sqA, (long long)L.ntc * chunk); DA(L.dotA, (long long)L.ntc * chunk); DA(L.sqRA, (long long)L.ntc * chunk);
             DA(L.mean, chunk); DA(L.vr, chunk); DA(L.gm, chunk); DA(L.gv, chunk);
             DA(L.kg_partial, (long long)c->kg_slots * (2 + 2 * D) * Mp);
-            // SYRK split count: fill the 148 SMs with (lower tiles) x (splits); each split a multiple of 16 rows of a 512-multiple
+            // SYRK split count: (lower tiles) x (splits) CTAs should fill whole waves of 148 SMs x SMINB resident CTAs
+            // (profiles/ncu_syrk_r01_v2.txt: 1.23 waves cost 20 %); pick the split count with the best fill, ties -> fewer splits
             const int nts = L.Mp / ZIGP_SBT, tiles = nts * (nts + 1) / 2;
-            int ns = 1;
-            while (ns < 512 / KT && tiles * ns < 148 * ZIGP_SMINB) ns *= 2;   // every split stays a multiple of KT rows
+            const int slots = 148 * ZIGP_SMINB;
+            int ns = 1; double best = 0.0;
+            for (int cand = 1; cand <= 16; cand++) {
+                const long long ctas = (long long)tiles * cand;
+                const double fill = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+                if (fill > best + 0.02) { best = fill; ns = cand; }
+            }
             L.nsplit = ns;
             DA(L.E_splits, (long long)ns * MM);
         }
