@@ -56,6 +56,17 @@ int zigp_destroy(zigp_ctx* ctx);
 const char* zigp_last_error(const zigp_ctx* ctx);   /* ctx may be NULL: error of the last failed zigp_create */
 int64_t zigp_theta_len(const zigp_ctx* ctx);
 
+/* Kronecker (space (x) time) inducing-grid variant: the objective of scripts/onoff.py:143-319 (build_prior_kl :143-159 /
+ * GaussKLkron onofftf/main.py:350-387, kron_inf :186-213, build_predict :161-184, cost :286-319) with K = Ks (x) Kt per latent,
+ * Ms_* spatial x Mt_* temporal inducing points, the first Ds input columns feeding the spatial kernel and the next Dt the
+ * temporal one (_gen_inp_mask :243-250), flattened inducing index m = i_space * Mt + i_time (:206), per-factor jitter (:18).
+ * Every other entry point of this header then works on the returned context unchanged (set_data, elbo_grad, accumulate /
+ * accum_buffer / finish, prior_kl, predict, ...), with
+ *   theta = for latent f then g: [ell_s[Ds], var_s, ell_t[Dt], var_t], noise_var,
+ *           Zf_s[Ms_f*Ds], Zf_t[Mt_f*Dt], Zg_s[Ms_g*Ds], Zg_t[Mt_g*Dt], u_fm[Ms_f*Mt_f], u_gm[..], u_fs_sqrt[..], u_gs_sqrt[..]
+ *   out[3] info: k > 0 -> pivot (k-1) % 2^20 of factor ((k-1) >> 20) & 1 (0 = space, 1 = time) of latent (k-1) >> 21. */
+int zigp_create_kron(zigp_ctx** ctx, int device, int Ms_f, int Mt_f, int Ms_g, int Mt_g, int Ds, int Dt, double jitter, int64_t chunk_rows);
+
 /* Attach this rank's shard of the minibatch: X (n_local x D), Y (n_local).  scale = num_data / global batch size
  * (onoffgpf/OnOffSVGP.py:119-120).  Device pointers are borrowed until the next set_data / destroy. */
 int zigp_set_data_dev(zigp_ctx* ctx, const double* X_dev, const double* Y_dev, int64_t n_local, double scale);

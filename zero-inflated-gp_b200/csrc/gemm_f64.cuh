@@ -19,6 +19,9 @@ namespace zigp {
 #ifndef ZIGP_KT
 #define ZIGP_KT 32
 #endif
+#ifndef ZIGP_RASTER
+#define ZIGP_RASTER 1
+#endif
 constexpr int KT = ZIGP_KT;     // k-slab depth (doubles) staged per pipeline stage
 constexpr int SPAD = 4;         // row padding -> stride 20 doubles == 4 (mod 16): DMMA fragment loads hit 32 distinct banks
 constexpr int SSTR = KT + SPAD;
@@ -37,6 +40,7 @@ struct GemmArgs {
     //   stat_sq[ct*rows + r]  = sum_{c in tile} Out[r,c]^2
     //   stat_dot[ct*rows + r] = sum_{c in tile} Out[r,c] * dotvec[c]
     double* stat_sq; double* stat_dot; const double* dotvec;
+    double* OutSq;                      // optional second output: Out[r,c]^2, same ld as Out (Kronecker path: w*w, u*u)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -76,11 +80,22 @@ gemm_tn_f64(const GemmArgs g) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % C::WARPS_M, wn = warp / C::WARPS_M;
 
-    // tile coordinates.  blockIdx.x runs over row tiles fastest; column tiles are visited heaviest-first so that the
-    // short triangular tiles fill the tail of the last wave.
+    // tile coordinates.
     const int ntr = g.rows / BM, ntc = g.cols / BN;
+    (void)ntr;
+#if ZIGP_RASTER == 0
+    // row tiles fastest; column tiles heaviest-first so that the short triangular tiles fill the tail of the last wave.
+    // Every resident CTA then streams a different row tile of In: In is re-read from DRAM once per column tile
+    // (profiles/ncu_gemm_r01_v3.txt: 4.5 GB read per launch against 0.52 GB algorithmic).
     int tr = blockIdx.x % ntr;
     int tcx = blockIdx.x / ntr;
+#else
+    // column tiles fastest: the ~444 resident CTAs cover ~28 row tiles x all column tiles, so a 64-row slab of In
+    // (64 x kdim x 8 B = 512 KB at kdim 1024) is fetched from DRAM once and re-used from L2 by its ntc column tiles;
+    // the M x M factor (8 MB) stays L2-resident throughout.
+    int tcx = blockIdx.x % ntc;
+    int tr = blockIdx.x / ntc;
+#endif
     int tc = (g.tri == TRI_LOWER) ? (ntc - 1 - tcx) : tcx;   // LOWER: last column tile has the longest k-range
     const int row0 = tr * BM, col0 = tc * BN;
 
@@ -196,6 +211,7 @@ gemm_tn_f64(const GemmArgs g) {
                 v0 += g.beta * z.x; v1 += g.beta * z.y;
             }
             *reinterpret_cast<double2*>(g.Out + (long long)r * g.ldo + c) = make_double2(v0, v1);
+            if (g.OutSq) *reinterpret_cast<double2*>(g.OutSq + (long long)r * g.ldo + c) = make_double2(v0 * v0, v1 * v1);
             if (stats) {
                 ssq = fma(v0, v0, ssq); ssq = fma(v1, v1, ssq);
                 sdt = fma(v0, dv[j][0], sdt); sdt = fma(v1, dv[j][1], sdt);
@@ -249,6 +265,8 @@ struct SyrkArgs {
     const double* Aw; const double* A; long long lda;    // n x m each: Aw = diag(w) A (row-scaled copy), A
     double* E; long long ldE; long long split_stride;   // [nsplit][m x m]
     int n, m, nsplit;
+    // rectangular mode (FULL = true, Kronecker path):  E[i,j] += sum_n Aw[n,i] A[n,j],  Aw: n x m (ld lda), A: n x mj (ld ldb)
+    long long ldb; int mj;
 };
 
 template <int BT, int WM, int WN, int STAGES, int MINB = 1>
@@ -260,7 +278,7 @@ struct NtCfg {
     static constexpr size_t SMEM = (size_t)STAGES * (2 * KT * STR) * sizeof(double);
 };
 
-template <int BT, int WM, int WN, int STAGES, int MINB = 1>
+template <int BT, int WM, int WN, int STAGES, int MINB = 1, bool FULL = false>
 __global__ void __launch_bounds__(NtCfg<BT, WM, WN, STAGES, MINB>::THREADS, MINB)
 syrk_nt_f64(const SyrkArgs g) {
     using C = NtCfg<BT, WM, WN, STAGES, MINB>;
@@ -269,12 +287,18 @@ syrk_nt_f64(const SyrkArgs g) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % C::WARPS_M, wn = warp / C::WARPS_M;
 
-    // lower-triangular tile index -> (ti, tj), ti >= tj
-    int t = blockIdx.x;
-    int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-    while (ti * (ti + 1) / 2 > t) ti--;
-    const int tj = t - ti * (ti + 1) / 2;
+    int ti, tj;
+    if (FULL) {                                 // every (ti, tj) tile of an m x mj output
+        const int ntj = g.mj / BT;
+        ti = blockIdx.x / ntj; tj = blockIdx.x % ntj;
+    } else {                                    // lower-triangular tile index -> (ti, tj), ti >= tj
+        int t = blockIdx.x;
+        ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        tj = t - ti * (ti + 1) / 2;
+    }
+    const long long ldb = FULL ? g.ldb : g.lda;
     const int split = blockIdx.y;
     // the n/KT slabs are dealt to the splits as evenly as integers allow
     const long long S = g.n / KT;
@@ -290,7 +314,7 @@ syrk_nt_f64(const SyrkArgs g) {
         for (int c = tid; c < KT * CH; c += C::THREADS) {
             int r = c / CH, q = c % CH;
             cp_async16(dI + r * C::STR + q * 2, g.Aw + (long long)(nn + r) * g.lda + i0 + q * 2);
-            cp_async16(dJ + r * C::STR + q * 2, g.A + (long long)(nn + r) * g.lda + j0 + q * 2);
+            cp_async16(dJ + r * C::STR + q * 2, g.A + (long long)(nn + r) * ldb + j0 + q * 2);
         }
     };
 
@@ -345,10 +369,10 @@ syrk_nt_f64(const SyrkArgs g) {
     }
 }
 
-template <int BT, int WM, int WN, int STAGES, int MINB = 1>
+template <int BT, int WM, int WN, int STAGES, int MINB = 1, bool FULL = false>
 inline cudaError_t launch_syrk_nt(const SyrkArgs& g, cudaStream_t st) {
     using C = NtCfg<BT, WM, WN, STAGES, MINB>;
-    auto kern = syrk_nt_f64<BT, WM, WN, STAGES, MINB>;
+    auto kern = syrk_nt_f64<BT, WM, WN, STAGES, MINB, FULL>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -356,7 +380,7 @@ inline cudaError_t launch_syrk_nt(const SyrkArgs& g, cudaStream_t st) {
         attr_done = true;
     }
     int nt = g.m / BT;
-    dim3 grid(nt * (nt + 1) / 2, g.nsplit);
+    dim3 grid(FULL ? nt * (g.mj / BT) : nt * (nt + 1) / 2, g.nsplit);
     kern<<<grid, C::THREADS, C::SMEM, st>>>(g);
     return cudaGetLastError();
 }

@@ -6,10 +6,13 @@
 namespace zigp {
 
 // K[n, m] = var * exp(-0.5 * sum_d ((x_nd - z_md)/ell_d)^2)   for n < nvalid, m < M ; 0 in the padding.
+// x_n = X[n*xstride + xoff .. + D): the dense path passes (D, 0); a Kronecker factor reads its own column group
+// (scripts/onoff.py:243-250).
 // Point-major (m contiguous) so that every later contraction reads k-contiguous operands.  (onofftf/main.py:53-57)
 __global__ void __launch_bounds__(256) kgen_kernel(const double* __restrict__ X, const double* __restrict__ Z,
                                                    const double* __restrict__ ell, const double* __restrict__ var, long long n0,
-                                                   int nvalid, int rows, int M, int D, int Mp, double* __restrict__ K) {
+                                                   int nvalid, int rows, int M, int D, int Mp, double* __restrict__ K,
+                                                   int xstride, int xoff) {
     __shared__ double sx[8][ZIGP_MAX_D];
     const int m = blockIdx.x * 32 + (threadIdx.x & 31);
     const int rl = threadIdx.x >> 5;                 // 8 rows per pass
@@ -24,7 +27,7 @@ __global__ void __launch_bounds__(256) kgen_kernel(const double* __restrict__ X,
     for (int rr = rbeg; rr < rbeg + 64; rr += 8) {
         const int r = rr + rl;
         __syncthreads();
-        if ((threadIdx.x & 31) < D && r < nvalid) sx[rl][threadIdx.x & 31] = X[(n0 + r) * D + (threadIdx.x & 31)];
+        if ((threadIdx.x & 31) < D && r < nvalid) sx[rl][threadIdx.x & 31] = X[(n0 + r) * xstride + xoff + (threadIdx.x & 31)];
         __syncthreads();
         double out = 0.0;
         if (r < nvalid && m < M) {
@@ -107,6 +110,7 @@ struct PointArgs {
     double* mean[2]; double* vr[2];   // fmean/fvar, gmean/gvar
     double* gm[2]; double* gv[2];     // scale * d var_exp / d mean, d var
     double* partial;                  // [gridDim.x][4]: sum ll, scale*sum dnoise, sum gv_f, sum gv_g  (+= across chunks)
+    int precomputed;                  // 1: mean[]/vr[] already hold the moments (Kronecker path); 0: build them from the row stats
 };
 
 __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
         double mean[2], vr[2];
 #pragma unroll
         for (int l = 0; l < 2; l++) {
+            if (p.precomputed) { mean[l] = p.mean[l][r]; vr[l] = p.vr[l][r]; continue; }
             double sa = 0.0, da = 0.0, sra = 0.0;
             for (int t = 0; t < p.ntc[l]; t++) {      // fixed order: deterministic
                 sa += p.sqA[l][(long long)t * p.rows + r];

@@ -9,7 +9,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
-#include "nstage.cuh"
+#include "kron.cuh"
 
 using namespace zigp;
 
@@ -38,6 +38,32 @@ struct Latent {
     double *accE = nullptr, *accV = nullptr;
 };
 
+// Kronecker variant (kron_host.cuh): one factor (space or time) of one latent
+struct KFactor {
+    int M = 0, Mp = 0, nb = 0, ntc = 0, D = 0, xoff = 0;
+    long long off_ell = 0, off_var = 0, off_Z = 0;
+    // M-stage
+    double *Lb = nullptr, *Lt = nullptr, *T = nullptr, *Tt = nullptr, *Dinv = nullptr, *Dinvt = nullptr, *Xtmp = nullptr;
+    double *d = nullptr, *cvec = nullptr;                    // diag(K^-1), S2 d_other
+    double *TF = nullptr, *CC = nullptr, *Tc = nullptr, *TDT = nullptr, *H = nullptr, *Ut = nullptr, *G = nullptr;
+    double *gZ = nullptr, *pell = nullptr, *pvar = nullptr;
+    // N-stage (per chunk)
+    double *Kb = nullptr, *Ab = nullptr, *Ub = nullptr, *Vb = nullptr, *tmp = nullptr, *KVb = nullptr, *sq = nullptr, *p = nullptr;
+    double *kg_partial = nullptr, *F_splits = nullptr;
+    // accumulator views: FT = sum_n a v^T (Mp x Mp), vec = [S0, S1(D), Q2(D)] x Mp
+    double *accFT = nullptr, *accV = nullptr;
+};
+struct KLatent {
+    KFactor f[2];
+    int Ms = 0, Mt = 0, nsplit = 1;
+    long long off_mu = 0, off_s = 0;
+    double *Q = nullptr, *Qt = nullptr, *S2 = nullptr, *S2t = nullptr, *X1t = nullptr, *C = nullptr, *Ct = nullptr, *X2t = nullptr, *Ymu = nullptr, *kl = nullptr;
+    double *W2 = nullptr, *U2 = nullptr, *QW = nullptr, *SW = nullptr, *QtU = nullptr, *StU2 = nullptr, *P1 = nullptr, *P2 = nullptr;
+    double *mean = nullptr, *vr = nullptr, *gm = nullptr, *gv = nullptr;
+    double *Qbar_splits = nullptr, *S2bar_splits = nullptr;
+    double *accQbar = nullptr, *accS2bar = nullptr;
+};
+
 }  // namespace
 
 struct zigp_ctx {
@@ -63,6 +89,11 @@ struct zigp_ctx {
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int cat; };
     std::vector<ProfRec> prof;
+    // Kronecker variant
+    bool kron = false;
+    int Ds = 0, Dt = 0;
+    long long off_noise = 0;
+    KLatent klat[2];
 };
 
 namespace {
@@ -172,50 +203,65 @@ int gemmM(zigp_ctx* c, const double* In, long long ldi, const double* W, long lo
         if (r_) return r_;       \
     } while (0)
 
+struct CholBufs { double *Lb, *Lt, *T, *Tt, *Dinv, *Dinvt, *Xtmp; int Mp, nb; };
+
+// Lb holds Kmm + jitter I (padding = identity) on entry.  Blocked right-looking Cholesky (diagonal 64-blocks factorised and
+// inverted in shared memory, panels / trailing updates through the DMMA engine), then T = L^-1 by block columns.
+// On exit: Lb = L (upper part zero), Lt = L^T, T = L^-1, Tt = T^T.  A non-positive pivot is recorded in c->info as
+// (tag << 20) + pivot + 1.
+int chol_inverse(zigp_ctx* c, const CholBufs& b, int tag, cudaStream_t st) {
+    const int Mp = b.Mp;
+    const long long MM = (long long)Mp * Mp;
+    dim3 g2((Mp + 127) / 128, Mp);
+    // blocked right-looking Cholesky
+    for (int kb = 0; kb < b.nb; kb++) {
+        double* diag = b.Lb + (long long)kb * NB * (Mp + 1);
+        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, b.Dinv + (long long)kb * NB * NB, b.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, tag);
+        LAUNCHED();
+        const int rem = Mp - (kb + 1) * NB;
+        if (rem > 0) {
+            double* panel = b.Lb + (long long)(kb + 1) * NB * Mp + (long long)kb * NB;
+            RUN(gemmM(c, panel, Mp, b.Dinv + (long long)kb * NB * NB, NB, panel, Mp, nullptr, 0, 1.0, 0.0, rem, NB, NB, st));
+            double* trail = b.Lb + (long long)(kb + 1) * NB * (Mp + 1);
+            RUN(gemmM(c, panel, Mp, panel, Mp, trail, Mp, trail, Mp, -1.0, 1.0, rem, rem, NB, st));
+        }
+    }
+    zero_upper_kernel<<<g2, 128, 0, st>>>(b.Lb, Mp);
+    LAUNCHED();
+    dim3 gt(Mp / 32, Mp / 32), bt(32, 8);
+    transpose_kernel<<<gt, bt, 0, st>>>(b.Lb, b.Lt, Mp, nullptr);
+    LAUNCHED();
+    // T = L^-1 by block columns, last to first
+    CK(cudaMemsetAsync(b.T, 0, MM * sizeof(double), st));
+    for (int jb = b.nb - 1; jb >= 0; jb--) {
+        copy_block_kernel<<<1, 256, 0, st>>>(b.Dinv + (long long)jb * NB * NB, b.T + (long long)jb * NB * (Mp + 1), Mp);
+        LAUNCHED();
+        const int i0 = (jb + 1) * NB, rem = Mp - i0;
+        if (rem > 0) {
+            RUN(gemmM(c, b.T + (long long)i0 * Mp + i0, Mp, b.Lt + (long long)jb * NB * Mp + i0, Mp, b.Xtmp, NB, nullptr, 0, 1.0, 0.0, rem, NB, rem, st));
+            RUN(gemmM(c, b.Xtmp, NB, b.Dinvt + (long long)jb * NB * NB, NB, b.T + (long long)i0 * Mp + (long long)jb * NB, Mp, nullptr, 0, -1.0, 0.0, rem, NB, NB, st));
+        }
+    }
+    transpose_kernel<<<gt, bt, 0, st>>>(b.T, b.Tt, Mp, nullptr);
+    LAUNCHED();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
     ProfScope ps(c, PC_MFWD, st);
     Latent& L = c->lat[l];
     const int M = L.M, Mp = L.Mp, D = c->D;
-    const long long MM = (long long)Mp * Mp;
     dim3 g2((Mp + 127) / 128, Mp);
+    dim3 gt(Mp / 32, Mp / 32), bt(32, 8);
     kmm_build_kernel<<<g2, 128, 0, st>>>(theta + L.off_Z, theta + L.off_ell, theta + L.off_var, M, D, Mp, c->jitter, L.Lb);
     LAUNCHED();
     pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_mu, L.mu, M, Mp);
     LAUNCHED();
     pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_s, L.s, M, Mp);
     LAUNCHED();
-    // blocked right-looking Cholesky
-    for (int kb = 0; kb < L.nb; kb++) {
-        double* diag = L.Lb + (long long)kb * NB * (Mp + 1);
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, L.Dinv + (long long)kb * NB * NB, L.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, l);
-        LAUNCHED();
-        const int rem = Mp - (kb + 1) * NB;
-        if (rem > 0) {
-            double* panel = L.Lb + (long long)(kb + 1) * NB * Mp + (long long)kb * NB;
-            RUN(gemmM(c, panel, Mp, L.Dinv + (long long)kb * NB * NB, NB, panel, Mp, nullptr, 0, 1.0, 0.0, rem, NB, NB, st));
-            double* trail = L.Lb + (long long)(kb + 1) * NB * (Mp + 1);
-            RUN(gemmM(c, panel, Mp, panel, Mp, trail, Mp, trail, Mp, -1.0, 1.0, rem, rem, NB, st));
-        }
-    }
-    zero_upper_kernel<<<g2, 128, 0, st>>>(L.Lb, Mp);
-    LAUNCHED();
-    dim3 gt(Mp / 32, Mp / 32), bt(32, 8);
-    transpose_kernel<<<gt, bt, 0, st>>>(L.Lb, L.Lt, Mp, nullptr);
-    LAUNCHED();
-    // T = L^-1 by block columns, last to first
-    CK(cudaMemsetAsync(L.T, 0, MM * sizeof(double), st));
-    for (int jb = L.nb - 1; jb >= 0; jb--) {
-        copy_block_kernel<<<1, 256, 0, st>>>(L.Dinv + (long long)jb * NB * NB, L.T + (long long)jb * NB * (Mp + 1), Mp);
-        LAUNCHED();
-        const int i0 = (jb + 1) * NB, rem = Mp - i0;
-        if (rem > 0) {
-            RUN(gemmM(c, L.T + (long long)i0 * Mp + i0, Mp, L.Lt + (long long)jb * NB * Mp + i0, Mp, L.Xtmp, NB, nullptr, 0, 1.0, 0.0, rem, NB, rem, st));
-            RUN(gemmM(c, L.Xtmp, NB, L.Dinvt + (long long)jb * NB * NB, NB, L.T + (long long)i0 * Mp + (long long)jb * NB, Mp, nullptr, 0, -1.0, 0.0, rem, NB, NB, st));
-        }
-    }
-    transpose_kernel<<<gt, bt, 0, st>>>(L.T, L.Tt, Mp, nullptr);
-    LAUNCHED();
+    CholBufs cb{L.Lb, L.Lt, L.T, L.Tt, L.Dinv, L.Dinvt, L.Xtmp, Mp, L.nb};
+    RUN(chol_inverse(c, cb, l, st));
     colscale_kernel<<<g2, 128, 0, st>>>(L.T, L.Rt, Mp, L.s);
     LAUNCHED();
     transpose_kernel<<<gt, bt, 0, st>>>(L.Rt, L.R, Mp, nullptr);
@@ -239,7 +285,7 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
     dim3 gk(Mp / 32, rows / 64);
     {
         ProfScope ps(c, PC_KGEN, st);
-        kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb);
+        kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, c->D, 0);
         LAUNCHED();
     }
     GemmArgs g{};
@@ -424,6 +470,21 @@ __global__ void kl_out_kernel(const double* klf, const double* klg, const int* i
     out[1] = (double)info[0];
 }
 
+#include "kron_host.cuh"
+
+int do_accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) { return c->kron ? kron_accumulate(c, theta, st) : accumulate(c, theta, st); }
+int do_finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) { return c->kron ? kron_finish(c, theta, out, st) : finish(c, theta, out, st); }
+
+void not_pd_message(zigp_ctx* c, long long info) {
+    char b[200];
+    const long long k = info - 1, tag = k >> 20, piv = k & ((1 << 20) - 1);
+    if (c->kron)
+        snprintf(b, sizeof b, "zigp: Kmm + jitter*I of latent %s, %s factor, is not positive definite (pivot %lld)", (tag >> 1) ? "g" : "f", (tag & 1) ? "time" : "space", piv);
+    else
+        snprintf(b, sizeof b, "zigp: Kmm + jitter*I of latent %s is not positive definite (pivot %lld)", tag ? "g" : "f", piv);
+    c->err = b;
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -524,6 +585,40 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
     return ZIGP_OK;
 }
 
+int zigp_create_kron(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g, int Mt_g, int Ds, int Dt, double jitter, int64_t chunk_rows) {
+    if (!out) return ZIGP_EINVAL;
+    *out = nullptr;
+    const int lim = 1 << 14;
+    if (Ms_f <= 0 || Mt_f <= 0 || Ms_g <= 0 || Mt_g <= 0 || Ds <= 0 || Dt <= 0 || Ds > ZIGP_MAX_D || Dt > ZIGP_MAX_D || !(jitter >= 0.0) ||
+        Ms_f >= lim || Mt_f >= lim || Ms_g >= lim || Mt_g >= lim) {
+        g_create_error = "zigp_create_kron: bad argument (need 0 < Ms, Mt < 2^14, 0 < Ds, Dt <= 8, jitter >= 0)";
+        return ZIGP_EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = std::string("zigp_create_kron: no usable CUDA device (") + cudaGetErrorString(e) + "); libzigp has no CPU fallback";
+        return ZIGP_ECUDA;
+    }
+    zigp_ctx* c = new zigp_ctx();
+    c->device = device; c->kron = true; c->Ds = Ds; c->Dt = Dt; c->D = Ds + Dt; c->jitter = jitter;
+    auto fail = [&](int code) { g_create_error = c->err; zigp_destroy(c); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(ZIGP_ECUDA); }
+    int cc_major = 0;
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    if (cc_major != 10) { c->err = "libzigp is built for sm_100a (B200) only"; return fail(ZIGP_ECUDA); }
+    long long chunk = chunk_rows > 0 ? chunk_rows : 32768;
+    c->chunk = rup(chunk, 512);
+    const int Ms[2] = {Ms_f, Ms_g}, Mt[2] = {Mt_f, Mt_g};
+    { int r = kron_alloc(c, Ms, Mt); if (r) return fail(r); }
+    if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
+        c->err = "cudaFuncSetAttribute(potrf_diag_kernel) failed";
+        return fail(ZIGP_ECUDA);
+    }
+    *out = c;
+    return ZIGP_OK;
+}
+
 int zigp_destroy(zigp_ctx* c) {
     if (!c) return ZIGP_OK;
     cudaSetDevice(c->device);
@@ -570,7 +665,7 @@ int zigp_set_data_host(zigp_ctx* c, const double* X, const double* Y, int64_t n,
 
 int zigp_accumulate_dev(zigp_ctx* c, const double* theta, void* stream) {
     if (!c || !theta) return ZIGP_EINVAL;
-    return accumulate(c, theta, (cudaStream_t)stream);
+    return do_accumulate(c, theta, (cudaStream_t)stream);
 }
 
 int zigp_accum_buffer(zigp_ctx* c, double** buf, int64_t* len) {
@@ -581,13 +676,13 @@ int zigp_accum_buffer(zigp_ctx* c, double** buf, int64_t* len) {
 
 int zigp_finish_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
     if (!c || !theta || !out) return ZIGP_EINVAL;
-    return finish(c, theta, out, (cudaStream_t)stream);
+    return do_finish(c, theta, out, (cudaStream_t)stream);
 }
 
 int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
     if (!c || !theta || !out) return ZIGP_EINVAL;
-    RUN(accumulate(c, theta, (cudaStream_t)stream));
-    return finish(c, theta, out, (cudaStream_t)stream);
+    RUN(do_accumulate(c, theta, (cudaStream_t)stream));
+    return do_finish(c, theta, out, (cudaStream_t)stream);
 }
 
 int zigp_elbo_grad_host(zigp_ctx* c, const double* theta, double* out, void* stream) {
@@ -596,16 +691,13 @@ int zigp_elbo_grad_host(zigp_ctx* c, const double* theta, double* out, void* str
     CK(cudaSetDevice(c->device));
     memcpy(c->theta_pin, theta, (size_t)c->theta_len * sizeof(double));
     CK(cudaMemcpyAsync(c->theta_dev, c->theta_pin, (size_t)c->theta_len * sizeof(double), cudaMemcpyHostToDevice, st));
-    RUN(accumulate(c, c->theta_dev, st));
-    RUN(finish(c, c->theta_dev, c->out_dev, st));
+    RUN(do_accumulate(c, c->theta_dev, st));
+    RUN(do_finish(c, c->theta_dev, c->out_dev, st));
     CK(cudaMemcpyAsync(c->out_pin, c->out_dev, (size_t)(c->theta_len + ZIGP_OUT_HEADER) * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(out, c->out_pin, (size_t)(c->theta_len + ZIGP_OUT_HEADER) * sizeof(double));
     if (out[3] != 0.0) {
-        char b[160];
-        long long k = (long long)out[3] - 1;
-        snprintf(b, sizeof b, "zigp: Kmm + jitter*I of latent %s is not positive definite (pivot %lld)", (k >> 20) ? "g" : "f", k & ((1 << 20) - 1));
-        c->err = b;
+        not_pd_message(c, (long long)out[3]);
         return ZIGP_ENOTPD;
     }
     return ZIGP_OK;
@@ -614,6 +706,7 @@ int zigp_elbo_grad_host(zigp_ctx* c, const double* theta, double* out, void* str
 int zigp_prior_kl_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
     if (!c || !theta || !out) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->kron) return kron_prior_kl(c, theta, out, st);
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     for (int l = 0; l < 2; l++) RUN(mstage_forward(c, l, theta, st));
@@ -625,6 +718,7 @@ int zigp_prior_kl_dev(zigp_ctx* c, const double* theta, double* out, void* strea
 int zigp_predict_dev(zigp_ctx* c, const double* theta, const double* Xnew, int64_t n_new, double* out9, void* stream) {
     if (!c || !theta || !Xnew || !out9 || n_new <= 0) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->kron) return kron_predict(c, theta, Xnew, n_new, out9, st);
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     for (int l = 0; l < 2; l++) RUN(mstage_forward(c, l, theta, st));
@@ -662,6 +756,7 @@ int zigp_predict_host(zigp_ctx* c, const double* theta, const double* Xnew, int6
 
 int zigp_debug_buffer(zigp_ctx* c, const char* name, int latent, double** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
     if (!c || !name || latent < 0 || latent > 1 || !ptr || !rows || !cols || !ld) return ZIGP_EINVAL;
+    if (c->kron) { c->err = "zigp_debug_buffer: dense contexts only"; return ZIGP_EINVAL; }
     Latent& L = c->lat[latent];
     const std::string n(name);
     struct Ent { const char* nm; double* p; long long r, cdim, ldim; };
@@ -707,6 +802,18 @@ int zigp_flop_counts(const zigp_ctx* c, double* algorithmic, double* executed) {
     if (!c || !algorithmic || !executed) return ZIGP_EINVAL;
     double alg = 0.0, exe = 0.0;
     const double n = (double)c->n_local;
+    if (c->kron) {
+        // per point per latent 12 Ms Mt + 6 (Ms^2 + Mt^2) flop; executed: the same products at the padded sizes
+        // (8 Ms Mt for QW, SW, QtU, StU2; 4 Ms Mt for Qbar, S2bar; per factor 4 triangular products = 4 M^2, FT = 2 M^2)
+        for (int l = 0; l < 2; l++) {
+            const KLatent& L = c->klat[l];
+            const double ms = L.Ms, mt = L.Mt, msp = L.f[0].Mp, mtp = L.f[1].Mp;
+            alg += (12.0 * ms * mt + 6.0 * (ms * ms + mt * mt)) * n;
+            exe += (12.0 * msp * mtp + 6.0 * (msp * msp + mtp * mtp)) * n;
+        }
+        *algorithmic = alg; *executed = exe;
+        return ZIGP_OK;
+    }
     for (int l = 0; l < 2; l++) {
         const Latent& L = c->lat[l];
         alg += 6.0 * (double)L.M * L.M * n;                                    // 6 M^2 per point per latent

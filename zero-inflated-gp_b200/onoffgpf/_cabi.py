@@ -16,6 +16,7 @@ _lib = None
 SYMBOLS = {
     # name: (restype, argtypes)
     "zigp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
+    "zigp_create_kron": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
     "zigp_destroy": (C.c_int, [C.c_void_p]),
     "zigp_last_error": (C.c_char_p, [C.c_void_p]),
     "zigp_theta_len": (C.c_int64, [C.c_void_p]),
@@ -73,9 +74,13 @@ def check(ctx, rc):
 class Context:
     """Owns one zigp_ctx (one GPU)."""
 
-    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0):
+    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0, kron=None):
+        """dense context, or with kron=(Ms_f, Mt_f, Ms_g, Mt_g, Ds, Dt) the Kronecker variant (zigp_create_kron)"""
         self._h = C.c_void_p()
-        rc = lib().zigp_create(C.byref(self._h), int(device), int(Mf), int(Mg), int(D), float(jitter), int(chunk_rows))
+        if kron is None:
+            rc = lib().zigp_create(C.byref(self._h), int(device), int(Mf), int(Mg), int(D), float(jitter), int(chunk_rows))
+        else:
+            rc = lib().zigp_create_kron(C.byref(self._h), int(device), *[int(v) for v in kron], float(jitter), int(chunk_rows))
         if rc != 0:
             msg = lib().zigp_last_error(None)
             raise ZigpError("%s (code %d)" % (msg.decode() if msg else "zigp_create failed", rc))

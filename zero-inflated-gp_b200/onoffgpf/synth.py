@@ -83,3 +83,22 @@ def build_model(X, Y, p, **kw):
     m = OnOffSVGP(X, Y, kernf=kf, kerng=kg, likelihood=lik, Zf=p["Zf"], Zg=p["Zg"], **kw)
     m.u_fm = p["u_fm"]; m.u_gm = p["u_gm"]; m.u_fs_sqrt = p["u_fs_sqrt"]; m.u_gs_sqrt = p["u_gs_sqrt"]
     return m
+
+
+# ---- Kronecker (space (x) time) variant: scripts/onoff.py parameterisation ---------------------------------------------
+def make_kron_params(Ms: int, Mt: int, Ds: int = 2, Dt: int = 1, seed: int = 0):
+    """per latent: spatial inducing points on a jittered Ds-dim grid, temporal ones on a jittered 1-D grid, lengthscales =
+    grid spacing, factor variances whose product is var_f = 1 / var_g = 5; q_mu = 0.01 randn, q_sqrt = 1 (flattened
+    m = i_space * Mt + i_time, scripts/onoff.py:206)."""
+    rng = np.random.default_rng(seed + 1)
+    p = {}
+    for lat, v in (("f", 1.0), ("g", 5.0)):
+        Zs, hs = inducing_grid(Ms, Ds, rng)
+        Zt, ht = inducing_grid(Mt, Dt, rng)
+        p[lat + "kell_s"], p[lat + "kell_t"] = hs.copy(), ht.copy()
+        p[lat + "kvar_s"], p[lat + "kvar_t"] = float(np.sqrt(v)), float(np.sqrt(v))
+        p["Z%s_s" % lat], p["Z%s_t" % lat] = Zs, Zt
+        p["u_%sm" % lat] = 0.01 * rng.standard_normal((Ms * Mt, 1))
+        p["u_%ss_sqrt" % lat] = np.ones((Ms * Mt, 1))
+    p["noisevar"] = 0.01
+    return p
