@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--dims", dest="d", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1 << 13, help="points per CPU-baseline evaluation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="dense", choices=["dense", "kron"],
+                    help="dense: BASELINE.json configs[3] (the headline); kron: configs[4], Kronecker inducing grid Ms x Mt = 64 x 64 (secondary line)")
+    ap.add_argument("--ms", type=int, default=64)
+    ap.add_argument("--mt", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0)
     return ap.parse_args()
 
@@ -108,9 +112,35 @@ def cpu_oracle_rate(N_sample, M, D, steps, warmup, threads=None):
     return N_sample / dt, dt, torch.get_num_threads()
 
 
+def cpu_kron_rate(N_sample, Ms, Mt, steps, warmup):
+    """points/sec of the float64 CPU restatement of the Kronecker trainer (oracle/kron_oracle.py: explicit factor inverses, dense
+    kron(K0^-1, K1^-1) @ Kmn as in scripts/onoff.py:186-213, autograd backward) on a bounded sample."""
+    from onoffgpf import synth
+    from oracle import kron_oracle as kro
+    X, Y = synth.make_data(N_sample, 3, seed=0)
+    p = kro.as_params(**synth.make_kron_params(Ms, Mt, 2, 1, seed=0))
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        kro.elbo_and_grads(X, Y, p, num_data=N_sample)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts[warmup:]))
+    return N_sample / dt, dt, torch.get_num_threads()
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if a.workload == "kron":
+        ns = min(a.cpu_sample, 1024)
+        rate, dt, threads = cpu_kron_rate(ns, a.ms, a.mt, max(1, a.steps), max(1, a.warmup))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "Kronecker inducing grid %dx%d, synthetic 2+1-D zero-inflated, fp64" % (a.ms, a.mt), "N": a.n, "Ms": a.ms, "Mt": a.mt},
+                          "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                           "sample": "N_b=%d points per step (dense kron(K0^-1,K1^-1) @ Kmn as in scripts/onoff.py:207)" % ns},
+                          "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     rate, dt, threads = cpu_oracle_rate(a.cpu_sample, a.m, a.d, max(1, a.steps), max(1, a.warmup))
     sample = "N_b=%d points of the same synthetic workload per step (Kmn is materialised, so the full N does not fit); float64" % a.cpu_sample
@@ -160,11 +190,24 @@ def run_ours(a):
     n_loc = hi - lo
 
     # synthetic data: generated per shard with a shard-specific seed (no rank needs the whole 2^24 x 3 array)
+    kron = a.workload == "kron"
+    if kron:
+        D = 3
     X, Y = synth.make_data(n_loc, D, seed=1000 + rank)
-    p = synth.make_params(M, M, D, seed=0)
     Xh = torch.as_tensor(X).pin_memory(); Yh = torch.as_tensor(Y.reshape(-1)).pin_memory()
-    theta_h = torch.as_tensor(synth.pack_theta(p)).pin_memory()
-    m = synth.build_model(Xh.numpy(), Yh.numpy().reshape(-1, 1), p, device=dev, distributed=(world > 1), chunk_rows=(a.chunk or None))
+    if kron:
+        from onofftf import OnOffKron
+        p = synth.make_kron_params(a.ms, a.mt, 2, 1, seed=0)
+        m = OnOffKron(Xh.numpy(), Yh.numpy().reshape(-1, 1), [p["Zf_s"], p["Zf_t"]], [p["Zg_s"], p["Zg_t"]], [p["fkell_s"], p["fkell_t"]],
+                      [p["fkvar_s"], p["fkvar_t"]], [p["gkell_s"], p["gkell_t"]], [p["gkvar_s"], p["gkvar_t"]], noisevar=p["noisevar"],
+                      u_fm=p["u_fm"], u_fs_sqrt=p["u_fs_sqrt"], u_gm=p["u_gm"], u_gs_sqrt=p["u_gs_sqrt"], device=dev, distributed=(world > 1),
+                      chunk_rows=(a.chunk or None))
+        with torch.no_grad():
+            theta_h = m.pack_theta().cpu().pin_memory()
+    else:
+        p = synth.make_params(M, M, D, seed=0)
+        theta_h = torch.as_tensor(synth.pack_theta(p)).pin_memory()
+        m = synth.build_model(Xh.numpy(), Yh.numpy().reshape(-1, 1), p, device=dev, distributed=(world > 1), chunk_rows=(a.chunk or None))
     ctx = m._ctx
     theta = theta_h.to(dev)
     out = torch.empty(ctx.out_len, dtype=torch.float64, device=dev)
@@ -251,10 +294,20 @@ def run_ours(a):
     # M x M triangular factor: M^2 flop per point (each of the six products per latent is M^2 flop)
     flops_per_launch = float(M) * M * (n_loc / max(1, gemm_n / 8))      # 8 launches per chunk (4 per latent)
     achieved = flops_per_launch / (gemm_ms / max(1, gemm_n) * 1e-3) * 1e-12 if gemm_n else 0.0
+    if kron:
+        # per point and latent the contraction class runs 8 triangular factor products (Ms^2 or Mt^2 flop each) and 4 full
+        # Ms x Mt products (2 Ms Mt flop each); the rate is averaged over all of them
+        gflop = 2.0 * (4.0 * (a.ms ** 2 + a.mt ** 2) + 8.0 * a.ms * a.mt) * n_loc
+        achieved = gflop / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else 0.0
 
     if rank == 0:
         cpu = None
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and kron:
+            ns = min(a.cpu_sample, 1024)
+            rate, dt, threads = cpu_kron_rate(ns, a.ms, a.mt, steps=3, warmup=1)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "3 timed ELBO+grad evaluations of N_b=%d points (dense kron(K0^-1,K1^-1) @ Kmn as in scripts/onoff.py:207); median %.2f s each" % (ns, dt)}
+        elif not a.no_cpu_baseline:
             rate, dt, threads = cpu_oracle_rate(a.cpu_sample, M, D, steps=3, warmup=1)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "3 timed ELBO+grad evaluations of N_b=%d points (same generator, same M, D); median %.2f s each" % (a.cpu_sample, dt)}
@@ -263,17 +316,19 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": ("BASELINE.json configs[3]: synthetic 3-D spatio-temporal zero-inflated, N=2^24 total, M=1024 per latent, RBF-ARD, fp64"
+            "config": {"workload": (("BASELINE.json configs[4] (secondary line, not the headline): Kronecker inducing grid %d x %d (space x time), synthetic 2+1-D zero-inflated, N=%d, fp64" % (a.ms, a.mt, N))
+                                    if kron else "BASELINE.json configs[3]: synthetic 3-D spatio-temporal zero-inflated, N=2^24 total, M=1024 per latent, RBF-ARD, fp64"
                                     if named else "synthetic zero-inflated N=%d D=%d M=%d fp64 (dev override, not the named config)" % (N, D, M)),
                        "N": N, "M": M, "D": D, "parallelism": "data-parallel over points, dp%d, one allreduce of %d doubles per step" % (world, ctx.accum_buffer()[1]),
-                       "l2": "inputs (X,Y %.0f MB) and per-chunk intermediates (%.0f MB) exceed the 126 MB L2; no explicit flush" % (n_loc * (D + 1) * 8 / 1e6, 64 * ctx_chunk_bytes(m) / 1e6),
+                       "l2": ("inputs (X,Y %.0f MB) exceed the 126 MB L2; no explicit flush" % (n_loc * (D + 1) * 8 / 1e6)) if kron else
+                             "inputs (X,Y %.0f MB) and per-chunk intermediates (%.0f MB) exceed the 126 MB L2; no explicit flush" % (n_loc * (D + 1) * 8 / 1e6, 64 * ctx_chunk_bytes(m) / 1e6),
                        "elbo": float(oh[0])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "note": "zigp_set_data_host + accumulate/finish + D2H of the packed ELBO/gradient, pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic_per_launch(M, ctx_chunk_rows(m)) if not kron else None,
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue ceiling 37.1 TFLOP/s, profiles/microbench)",
                          "whole_step_algorithmic_tflops": alg * world / (ms_step * 1e-3) * 1e-12 if world == 1 else None,
                          "whole_step_frac": (alg / (ms_step * 1e-3) * 1e-12 / peak_tf) if (world == 1 and peak_tf) else None,
@@ -284,6 +339,22 @@ def run_ours(a):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ctx_chunk_rows(m):
+    return m._ctx.debug_buffer("K", 0)[1]
+
+
+def traffic_per_launch(M, chunk_rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tn_f64 launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json; taken at M=1024, 65536 rows per launch) -- null for any other shape"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if (M, chunk_rows) == (t["M"], t["rows_per_launch"]):
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def ctx_chunk_bytes(m):

@@ -149,3 +149,37 @@ def elbo_and_grads(X, Y, p, num_data=None, jitter=1e-5):
     scale = (num_data or N) / N
     st, _ = accumulate(X, Y, p, scale, jitter)
     return finish(st, p, scale, jitter)
+
+
+def _flat_keys(st):
+    keys = []
+    for lat in ("f", "g"):
+        for k in ("Qbar", "S2bar", "Fs", "Ft", "sgv"):
+            keys.append((lat, k, None))
+        for fk in ("ks", "kt"):
+            for k in ("S0", "S1", "Q2"):
+                keys.append((lat, fk, k))
+    return keys
+
+
+def pack_stats(st):
+    """the additive per-shard statistics as one flat buffer (what one rank all-reduces)"""
+    parts = [st["ll"].reshape(1), st["dnoise"].reshape(1)]
+    for lat, a, b in _flat_keys(st):
+        v = st[lat][a] if b is None else st[lat][a][b]
+        parts.append(v.reshape(-1))
+    return torch.cat(parts)
+
+
+def unpack_stats(buf, like):
+    out = {"ll": buf[0], "dnoise": buf[1], "f": {"ks": {}, "kt": {}}, "g": {"ks": {}, "kt": {}}}
+    o = 2
+    for lat, a, b in _flat_keys(like):
+        ref = like[lat][a] if b is None else like[lat][a][b]
+        v = buf[o:o + ref.numel()].reshape(ref.shape)
+        o += ref.numel()
+        if b is None:
+            out[lat][a] = v
+        else:
+            out[lat][a][b] = v
+    return out

@@ -20,7 +20,7 @@ namespace zigp {
 #define ZIGP_KT 32
 #endif
 #ifndef ZIGP_RASTER
-#define ZIGP_RASTER 1
+#define ZIGP_RASTER 0
 #endif
 constexpr int KT = ZIGP_KT;     // k-slab depth (doubles) staged per pipeline stage
 constexpr int SPAD = 4;         // row padding -> stride 20 doubles == 4 (mod 16): DMMA fragment loads hit 32 distinct banks
@@ -84,17 +84,25 @@ gemm_tn_f64(const GemmArgs g) {
     const int ntr = g.rows / BM, ntc = g.cols / BN;
     (void)ntr;
 #if ZIGP_RASTER == 0
-    // row tiles fastest; column tiles heaviest-first so that the short triangular tiles fill the tail of the last wave.
-    // Every resident CTA then streams a different row tile of In: In is re-read from DRAM once per column tile
-    // (profiles/ncu_gemm_r01_v3.txt: 4.5 GB read per launch against 0.52 GB algorithmic).
+    // row tiles fastest over the whole launch; column tiles heaviest-first so that the short triangular tiles fill the tail
+    // of the last wave.  Every resident CTA streams a different row tile of In: In is re-read from DRAM once per column
+    // tile (profiles/ncu_gemm_r01_v3.txt: 4.5 GB read per launch against 0.52 GB algorithmic).
     int tr = blockIdx.x % ntr;
     int tcx = blockIdx.x / ntr;
-#else
-    // column tiles fastest: the ~444 resident CTAs cover ~28 row tiles x all column tiles, so a 64-row slab of In
-    // (64 x kdim x 8 B = 512 KB at kdim 1024) is fetched from DRAM once and re-used from L2 by its ntc column tiles;
-    // the M x M factor (8 MB) stays L2-resident throughout.
+#elif ZIGP_RASTER == 1
+    // column tiles fastest: minimal DRAM traffic, but the last wave mixes long and short tiles (2 % slower, profiles/raster_ab_r01.txt)
     int tcx = blockIdx.x % ntc;
     int tr = blockIdx.x / ntc;
+#else
+    // super-tiles: groups of RG row tiles; inside a group row tiles run fastest and column tiles heaviest-first.  A group's
+    // slab of In (RG x 64 rows x kdim x 8 B = 16 MB at kdim 1024) stays L2-resident while its column tiles are visited, so In is
+    // fetched from DRAM once, and the launch still ends on the shortest tiles.
+    constexpr int RG = 32;
+    const int per_group = RG * ntc;
+    const int grp = blockIdx.x / per_group, rem = blockIdx.x % per_group;
+    const int rows_in_group = min(RG, ntr - grp * RG);
+    int tcx = rem / rows_in_group;
+    int tr = grp * RG + rem % rows_in_group;
 #endif
     int tc = (g.tri == TRI_LOWER) ? (ntc - 1 - tcx) : tcx;   // LOWER: last column tile has the longest k-range
     const int row0 = tr * BM, col0 = tc * BN;
