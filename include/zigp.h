@@ -97,6 +97,11 @@ int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xne
 /* Test / profiling hooks: view of an internal device buffer after the last call.
  * name: "L","T","Kmm","alpha_w","beta","E","a","G","K","A","RA","V","Y","mean","var","gm","gv" ; latent 0 = f, 1 = g. */
 int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
+/* Test hook: one contraction Out[r,c] = sum_k In[r,k] W[c,k] (tri: 0 full, 1 lower k <= c, 2 upper k >= c; optional per-row,
+ * per-64-column-tile sums of squares) through engine 0 (DMMA, csrc/gemm_f64.cuh) or engine 1 (fp64 emulated on the int8 tensor
+ * cores, csrc/ozaki.cuh), so that the two engines can be compared on the same operands. */
+int zigp_debug_gemm(zigp_ctx* ctx, int engine, const double* In_dev, int64_t ldi, const double* W_dev, int64_t ldw, double* Out_dev, int64_t ldo,
+                    int rows, int cols, int kdim, int tri, double* stat_sq_dev, void* stream);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t zigp_launch_count(const zigp_ctx* ctx);
 /* Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).  Classes:

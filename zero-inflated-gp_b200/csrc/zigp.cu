@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "kron.cuh"
+#include "ozaki.cuh"
 
 using namespace zigp;
 
@@ -89,6 +90,9 @@ struct zigp_ctx {
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int cat; };
     std::vector<ProfRec> prof;
+    // scratch of zigp_debug_gemm (int8 engine)
+    int8_t *dbg_pa = nullptr, *dbg_pb = nullptr; double *dbg_sa = nullptr, *dbg_sb = nullptr;
+    size_t dbg_cap_a = 0, dbg_cap_b = 0, dbg_cap_r = 0, dbg_cap_c = 0;
     // Kronecker variant
     bool kron = false;
     int Ds = 0, Dt = 0;
@@ -626,6 +630,7 @@ int zigp_destroy(zigp_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->Xown) cudaFree(c->Xown);
     if (c->Yown) cudaFree(c->Yown);
+    cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
     if (c->theta_pin) cudaFreeHost(c->theta_pin);
     if (c->out_pin) cudaFreeHost(c->out_pin);
     delete c;
@@ -773,6 +778,44 @@ int zigp_debug_buffer(zigp_ctx* c, const char* name, int latent, double** ptr, i
         if (n == e.nm) { *ptr = e.p; *rows = e.r; *cols = e.cdim; *ld = e.ldim; return ZIGP_OK; }
     c->err = "zigp_debug_buffer: unknown buffer name";
     return ZIGP_EINVAL;
+}
+
+int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, const double* W, int64_t ldw, double* Out, int64_t ldo, int rows, int cols,
+                    int kdim, int tri, double* stat_sq, void* stream) {
+    if (!c || !In || !W || !Out || rows <= 0 || cols <= 0 || kdim <= 0 || tri < 0 || tri > 2) return ZIGP_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    if (engine == 0) {
+        if (rows % 64 || cols % 64 || kdim % 32) { c->err = "zigp_debug_gemm: DMMA engine needs rows, cols % 64 == 0 and kdim % 32 == 0"; return ZIGP_EINVAL; }
+        GemmArgs g{};
+        g.In = In; g.ldi = ldi; g.W = W; g.ldw = ldw; g.Out = Out; g.ldo = ldo; g.alpha = 1.0; g.beta = 0.0; g.rows = rows; g.cols = cols; g.kdim = kdim;
+        g.tri = tri; g.stat_sq = stat_sq;
+        return gemmN(c, g, st);
+    }
+    if (rows % oz::OBM || cols % oz::OBN || kdim % 128) { c->err = "zigp_debug_gemm: int8 engine needs rows % 128 == 0, cols % 64 == 0, kdim % 128 == 0"; return ZIGP_EINVAL; }
+    // scratch slice buffers live in the context (grown on demand) so that repeated calls time the kernels, not cudaMalloc;
+    // engine 2 = contraction only, re-using the slices of the previous engine-1 call with the same shapes
+    const size_t need_a = (size_t)oz::NSL * rows * kdim, need_b = (size_t)oz::NSL * cols * kdim;
+    if (need_a > c->dbg_cap_a || need_b > c->dbg_cap_b || (size_t)rows > c->dbg_cap_r || (size_t)cols > c->dbg_cap_c) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
+        c->dbg_pa = c->dbg_pb = nullptr; c->dbg_sa = c->dbg_sb = nullptr; c->dbg_cap_a = c->dbg_cap_b = c->dbg_cap_r = c->dbg_cap_c = 0;
+        CK(cudaMalloc((void**)&c->dbg_pa, need_a)); CK(cudaMalloc((void**)&c->dbg_pb, need_b));
+        CK(cudaMalloc((void**)&c->dbg_sa, (size_t)rows * 8)); CK(cudaMalloc((void**)&c->dbg_sb, (size_t)cols * 8));
+        c->dbg_cap_a = need_a; c->dbg_cap_b = need_b; c->dbg_cap_r = rows; c->dbg_cap_c = cols;
+        if (engine == 2) { c->err = "zigp_debug_gemm: engine 2 needs a preceding engine-1 call of the same shape"; return ZIGP_ESTATE; }
+    }
+    if (engine == 1) {
+        CK(oz::launch_slice_rows(In, ldi, rows, kdim, nullptr, c->dbg_pa, (long long)rows * kdim, c->dbg_sa, st));
+        CK(oz::launch_slice_rows(W, ldw, cols, kdim, nullptr, c->dbg_pb, (long long)cols * kdim, c->dbg_sb, st));
+        c->launches += 2;
+    }
+    oz::OzOperand A{c->dbg_pa, kdim, rows, (long long)rows * kdim, c->dbg_sa}, B{c->dbg_pb, kdim, cols, (long long)cols * kdim, c->dbg_sb};
+    oz::OzArgs g{};
+    g.Out = Out; g.ldo = ldo; g.alpha = 1.0; g.beta = 0.0; g.rows = rows; g.cols = cols; g.kdim = kdim; g.tri = tri; g.stat_sq = stat_sq; g.nsplit = 1;
+    CK(oz::launch_ozaki_gemm(A, B, g, st));
+    c->launches++;
+    return ZIGP_OK;
 }
 
 int zigp_set_profiling(zigp_ctx* c, int on) {
