@@ -97,6 +97,11 @@ int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xne
 /* Test / profiling hooks: view of an internal device buffer after the last call.
  * name: "L","T","Kmm","alpha_w","beta","E","a","G","K","A","RA","V","Y","mean","var","gm","gv" ; latent 0 = f, 1 = g. */
 int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
+/* Contraction engine of the dense path: 0 = DMMA (fp64 mma.sync, the default), 1 = fp64 emulated exactly-sliced on the INT8 tensor
+ * cores (tcgen05.mma kind::i8; csrc/ozaki.cuh: 8 x 7-bit slices per operand, int32 accumulation in TMEM, fp64 recombination --
+ * same worst-case error bound as an fp64 dot product, ~2x the DMMA rate).  Allocates the slice workspaces on first use. */
+int zigp_set_engine(zigp_ctx* ctx, int engine);
+int zigp_get_engine(const zigp_ctx* ctx);
 /* Test hook: one contraction Out[r,c] = sum_k In[r,k] W[c,k] (tri: 0 full, 1 lower k <= c, 2 upper k >= c; optional per-row,
  * per-64-column-tile sums of squares) through engine 0 (DMMA, csrc/gemm_f64.cuh) or engine 1 (fp64 emulated on the int8 tensor
  * cores, csrc/ozaki.cuh), so that the two engines can be compared on the same operands. */
@@ -106,9 +111,9 @@ int zigp_debug_gemm(zigp_ctx* ctx, int engine, const double* In_dev, int64_t ldi
 int64_t zigp_launch_count(const zigp_ctx* ctx);
 /* Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).  Classes:
  * 0 kgen (Kmn tiles), 1 gemm_tn (the four triangular contractions), 2 point (likelihood), 3 kgrad (Kmn-side gradient sums),
- * 4 syrk (E += A^T diag(gv) A), 5 M-stage forward, 6 M-stage backward, 7 slot reduction.  Off by default; switching it on or
+ * 4 syrk (E += A^T diag(gv) A), 5 M-stage forward, 6 M-stage backward, 7 slot reduction, 8 operand slicing (int8 engine).  Off by default; switching it on or
  * off clears the records.  zigp_profile_read synchronises the device. */
-#define ZIGP_PROFILE_CLASSES 8
+#define ZIGP_PROFILE_CLASSES 9
 int zigp_set_profiling(zigp_ctx* ctx, int on);
 int zigp_profile_read(zigp_ctx* ctx, double* ms_by_class, int64_t* launches_by_class, int n_classes);
 /* algorithmic flop count of one ELBO+grad evaluation of the current data shard (12 M^2 per point per SURVEY 8(d)) and

@@ -68,6 +68,60 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     }
 }
 
+// Transposed slicing for the rank update over the point dimension  E += Aw^T A :  X is n x m (point-major); the operands of the
+// contraction are the COLUMNS of X (k index = n), so the planes are written transposed, planes[p][c][n] (n contiguous), with one
+// power-of-two scale per column.  Pass 1: per-column max |x| (order-independent integer max on the bit pattern).
+__global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ X, long long ld, int n, int m, unsigned long long* __restrict__ colmax) {
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int r0 = blockIdx.y * 1024 + (threadIdx.x >> 6);
+    double mx = 0.0;
+    if (c < m)
+        for (int r = r0; r < min(n, (int)(blockIdx.y + 1) * 1024); r += 4) mx = fmax(mx, fabs(X[(long long)r * ld + c]));
+    __shared__ double sh[4][64];
+    sh[threadIdx.x >> 6][threadIdx.x & 63] = mx;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < m) {
+        mx = fmax(fmax(sh[0][threadIdx.x], sh[1][threadIdx.x]), fmax(sh[2][threadIdx.x], sh[3][threadIdx.x]));
+        atomicMax(colmax + c, (unsigned long long)__double_as_longlong(mx));      // non-negative doubles order like their bit patterns
+    }
+}
+
+// Pass 2: slice a 128 (n) x 32 (columns) tile per block and write it transposed.  n % 128 == 0, m % 32 == 0.
+__global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restrict__ X, long long ld, int n, int m,
+                                                          const unsigned long long* __restrict__ colmax, int8_t* __restrict__ planes,
+                                                          long long plane_stride, double* __restrict__ scale) {
+    __shared__ double tile[128][33];
+    const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 128;
+    for (int e = threadIdx.x; e < 128 * 32; e += 256) {
+        const int r = e >> 5, cc = e & 31;
+        tile[r][cc] = X[(long long)(n0 + r) * ld + c0 + cc];
+    }
+    __syncthreads();
+    // thread -> (column cc, 16 consecutive n): 32 columns x 8 groups of 16
+    const int cc = threadIdx.x >> 3, grp = threadIdx.x & 7;
+    const double mx = __longlong_as_double((long long)colmax[c0 + cc]);
+    int e = 0;
+    if (mx > 0.0) e = ilogb(mx) + 2;
+    const double inv = scalbn(1.0, -e);
+    if (blockIdx.y == 0 && grp == 0) scale[c0 + cc] = scalbn(1.0, e);
+    double t[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) t[j] = tile[grp * 16 + j][cc] * inv;
+    int8_t* out = planes + (long long)(c0 + cc) * n + n0 + grp * 16;
+#pragma unroll
+    for (int p = 0; p < NSL; p++) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const double sv = t[j] * 128.0;
+            const int q = __double2int_rn(sv);
+            t[j] = sv - (double)q;
+            w[j >> 2] |= (uint32_t)(q & 0xff) << (8 * (j & 3));
+        }
+        *reinterpret_cast<uint4*>(out + (long long)p * plane_stride) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // ---- the contraction ------------------------------------------------------------------------------------------------------
 struct OzArgs {
     const double* rscale;   // [rows]  2^e of the In rows
@@ -273,6 +327,16 @@ inline cudaError_t launch_ozaki_gemm(const OzOperand& A, const OzOperand& B, OzA
 inline cudaError_t launch_slice_rows(const double* X, long long ld, int rows, int K, const double* rowweight, int8_t* planes, long long plane_stride,
                                      double* scale, cudaStream_t st) {
     slice_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(X, ld, rows, K, rowweight, planes, plane_stride, scale);
+    return cudaGetLastError();
+}
+
+// planes[p][c][n] <- columns of X (n x m), scale[c]; colmax is an m-long scratch
+inline cudaError_t launch_slice_cols(const double* X, long long ld, int n, int m, unsigned long long* colmax, int8_t* planes, long long plane_stride,
+                                     double* scale, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(colmax, 0, (size_t)m * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    colmax_kernel<<<dim3((m + 63) / 64, (n + 1023) / 1024), 256, 0, st>>>(X, ld, n, m, colmax);
+    slice_cols_kernel<<<dim3(m / 32, n / 128), 256, 0, st>>>(X, ld, n, m, colmax, planes, plane_stride, scale);
     return cudaGetLastError();
 }
 

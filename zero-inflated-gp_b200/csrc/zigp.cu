@@ -37,6 +37,10 @@ struct Latent {
     int nsplit = 1;
     // accumulator views
     double *accE = nullptr, *accV = nullptr;
+    // int8 engine: slice planes + row scales of the four triangular factors (same order as ozW_src)
+    int8_t* ozW[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* ozWs[4] = {nullptr, nullptr, nullptr, nullptr};
+    int nsplit_oz = 4;
 };
 
 // Kronecker variant (kron_host.cuh): one factor (space or time) of one latent
@@ -90,6 +94,11 @@ struct zigp_ctx {
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int cat; };
     std::vector<ProfRec> prof;
+    // contraction engine: 0 = DMMA (gemm_f64.cuh), 1 = fp64 on the int8 tensor cores (ozaki.cuh); dense path only
+    int engine = 0;
+    int8_t *oz_in = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;     // slice planes: GEMM input (row-major), A / Aw transposed
+    double *oz_rs = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
+    unsigned long long* oz_colmax = nullptr;
     // scratch of zigp_debug_gemm (int8 engine)
     int8_t *dbg_pa = nullptr, *dbg_pb = nullptr; double *dbg_sa = nullptr, *dbg_sb = nullptr;
     size_t dbg_cap_a = 0, dbg_cap_b = 0, dbg_cap_r = 0, dbg_cap_c = 0;
@@ -121,7 +130,7 @@ namespace {
 
 inline long long rup(long long x, long long a) { return (x + a - 1) / a * a; }
 
-enum ProfCat { PC_KGEN = 0, PC_GEMM = 1, PC_POINT = 2, PC_KGRAD = 3, PC_SYRK = 4, PC_MFWD = 5, PC_MBWD = 6, PC_REDUCE = 7, PC_COUNT = 8 };
+enum ProfCat { PC_KGEN = 0, PC_GEMM = 1, PC_POINT = 2, PC_KGRAD = 3, PC_SYRK = 4, PC_MFWD = 5, PC_MBWD = 6, PC_REDUCE = 7, PC_SLICE = 8, PC_COUNT = 9 };
 
 struct ProfScope {
     zigp_ctx* c; cudaStream_t st; bool on; cudaEvent_t a{}, b{}; int cat;
@@ -185,7 +194,35 @@ int dalloc(zigp_ctx* c, double** p, long long n) {
 #define ZIGP_STAGES 2
 #endif
 
+// int8 engine: is g.W one of the pre-sliced triangular factors?
+bool oz_lookup(zigp_ctx* c, const double* W, int8_t** planes, double** scale, int* Mp) {
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        const double* src[4] = {L.T, L.R, L.Rt, L.Tt};
+        for (int i = 0; i < 4; i++)
+            if (W == src[i] && L.ozW[i]) { *planes = L.ozW[i]; *scale = L.ozWs[i]; *Mp = L.Mp; return true; }
+    }
+    return false;
+}
+
 int gemmN(zigp_ctx* c, const GemmArgs& g, cudaStream_t st) {
+    int8_t* wp = nullptr; double* ws = nullptr; int Mp = 0;
+    if (c->engine == 1 && !c->kron && g.rows % oz::OBM == 0 && g.cols % oz::OBN == 0 && g.kdim % 128 == 0 && oz_lookup(c, g.W, &wp, &ws, &Mp)) {
+        {
+            ProfScope ps(c, PC_SLICE, st);
+            CK(oz::launch_slice_rows(g.In, g.ldi, g.rows, g.kdim, nullptr, c->oz_in, (long long)g.rows * g.kdim, c->oz_rs, st));
+            c->launches++;
+        }
+        oz::OzOperand A{c->oz_in, g.kdim, g.rows, (long long)g.rows * g.kdim, c->oz_rs};
+        oz::OzOperand B{wp, Mp, Mp, (long long)Mp * Mp, ws};
+        oz::OzArgs a{};
+        a.Out = g.Out; a.ldo = g.ldo; a.Zin = g.Zin; a.ldz = g.ldz; a.alpha = g.alpha; a.beta = g.beta; a.rows = g.rows; a.cols = g.cols; a.kdim = g.kdim;
+        a.tri = g.tri; a.stat_sq = g.stat_sq; a.stat_dot = g.stat_dot; a.dotvec = g.dotvec; a.OutSq = g.OutSq; a.nsplit = 1;
+        ProfScope ps(c, PC_GEMM, st);
+        CK(oz::launch_ozaki_gemm(A, B, a, st));
+        c->launches++;
+        return 0;
+    }
     ProfScope ps(c, PC_GEMM, st);
     CK((launch_gemm_tn<ZIGP_BM, ZIGP_BN, ZIGP_WM, ZIGP_WN, ZIGP_STAGES, ZIGP_MINB>(g, st)));
     c->launches++;
@@ -279,6 +316,13 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
     LAUNCHED();
     kl_kernel<<<1, 256, 0, st>>>(L.aw, L.s, L.dK, L.Lb, M, Mp, L.kl);
     LAUNCHED();
+    if (c->engine == 1) {
+        const double* src[4] = {L.T, L.R, L.Rt, L.Tt};
+        for (int i = 0; i < 4; i++) {
+            CK(oz::launch_slice_rows(src[i], Mp, Mp, Mp, nullptr, L.ozW[i], (long long)Mp * Mp, L.ozWs[i], st));
+            c->launches++;
+        }
+    }
     return 0;
 }
 
@@ -337,7 +381,7 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     CK(cudaMemsetAsync(c->pt_partial, 0, (size_t)c->pt_slots * 4 * sizeof(double), st));
     for (int l = 0; l < 2; l++) {
         Latent& L = c->lat[l];
-        CK(cudaMemsetAsync(L.E_splits, 0, (size_t)L.nsplit * L.Mp * L.Mp * sizeof(double), st));
+        CK(cudaMemsetAsync(L.E_splits, 0, (size_t)std::max(L.nsplit, L.nsplit_oz) * L.Mp * L.Mp * sizeof(double), st));
         CK(cudaMemsetAsync(L.kg_partial, 0, (size_t)c->kg_slots * (2 + 2 * D) * L.Mp * sizeof(double), st));
         RUN(mstage_forward(c, l, theta, st));
     }
@@ -357,6 +401,24 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
                 kgrad_kernel<<<gg, 128, 0, st>>>(k);
                 LAUNCHED();
             }
+            if (c->engine == 1) {
+                // E += Aw^T A on the int8 engine: the operands are the columns of Aw and A (k index = point), sliced transposed
+                {
+                    ProfScope ps(c, PC_SLICE, st);
+                    CK(oz::launch_slice_cols(L.Vb, L.Mp, rows, L.Mp, c->oz_colmax, c->oz_colAw, (long long)L.Mp * rows, c->oz_csAw, st));
+                    CK(oz::launch_slice_cols(L.Ab, L.Mp, rows, L.Mp, c->oz_colmax + L.Mp, c->oz_colA, (long long)L.Mp * rows, c->oz_csA, st));
+                    c->launches += 4;
+                }
+                oz::OzOperand A{c->oz_colAw, rows, L.Mp, (long long)L.Mp * rows, c->oz_csAw};
+                oz::OzOperand B{c->oz_colA, rows, L.Mp, (long long)L.Mp * rows, c->oz_csA};
+                oz::OzArgs a{};
+                a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
+                a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
+                ProfScope ps(c, PC_SYRK, st);
+                CK(oz::launch_ozaki_gemm(A, B, a, st));
+                c->launches++;
+                continue;
+            }
             SyrkArgs s{};
             s.Aw = L.Vb; s.A = L.Ab; s.lda = L.Mp; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
             s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
@@ -374,7 +436,7 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     for (int l = 0; l < 2; l++) {
         Latent& L = c->lat[l];
         long long MM = (long long)L.Mp * L.Mp;
-        reduce_slots_kernel<<<(unsigned)((MM + 255) / 256), 256, 0, st>>>(L.E_splits, MM, L.nsplit, L.accE, MM);
+        reduce_slots_kernel<<<(unsigned)((MM + 255) / 256), 256, 0, st>>>(L.E_splits, MM, c->engine == 1 ? L.nsplit_oz : L.nsplit, L.accE, MM);
         LAUNCHED();
         long long VL = (long long)(2 + 2 * D) * L.Mp;
         reduce_slots_kernel<<<(unsigned)((VL + 255) / 256), 256, 0, st>>>(L.kg_partial, VL, c->kg_slots, L.accV, VL);
@@ -576,7 +638,7 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
                 if (fill > best + 0.02) { best = fill; ns = cand; }
             }
             L.nsplit = ns;
-            DA(L.E_splits, (long long)ns * MM);
+            DA(L.E_splits, (long long)std::max(ns, L.nsplit_oz) * MM);
         }
         return 0;
     };
@@ -817,6 +879,34 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
     c->launches++;
     return ZIGP_OK;
 }
+
+int zigp_set_engine(zigp_ctx* c, int engine) {
+    if (!c || engine < 0 || engine > 1) return ZIGP_EINVAL;
+    if (c->kron && engine == 1) { c->err = "zigp_set_engine: the int8 engine serves the dense path only"; return ZIGP_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    if (engine == 1 && !c->oz_in) {
+        if (!oz::encode_fn()) { c->err = "zigp_set_engine: cuTensorMapEncodeTiled not available from this driver"; return ZIGP_ECUDA; }
+        const long long chunk = c->chunk;
+        long long Mpmax = std::max(c->lat[0].Mp, c->lat[1].Mp);
+        auto balloc = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, bytes)); c->allocs.push_back(*p); return 0; };
+        RUN(balloc((void**)&c->oz_in, (size_t)oz::NSL * chunk * Mpmax));
+        RUN(balloc((void**)&c->oz_colA, (size_t)oz::NSL * chunk * Mpmax));
+        RUN(balloc((void**)&c->oz_colAw, (size_t)oz::NSL * chunk * Mpmax));
+        RUN(balloc((void**)&c->oz_colmax, (size_t)2 * Mpmax * sizeof(unsigned long long)));
+        DA(c->oz_rs, chunk); DA(c->oz_csA, Mpmax); DA(c->oz_csAw, Mpmax);
+        for (int l = 0; l < 2; l++) {
+            Latent& L = c->lat[l];
+            for (int i = 0; i < 4; i++) {
+                RUN(balloc((void**)&L.ozW[i], (size_t)oz::NSL * L.Mp * L.Mp));
+                DA(L.ozWs[i], L.Mp);
+            }
+        }
+    }
+    c->engine = engine;
+    return ZIGP_OK;
+}
+
+int zigp_get_engine(const zigp_ctx* c) { return c ? c->engine : -1; }
 
 int zigp_set_profiling(zigp_ctx* c, int on) {
     if (!c) return ZIGP_EINVAL;

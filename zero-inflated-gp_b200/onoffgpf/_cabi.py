@@ -31,6 +31,8 @@ SYMBOLS = {
     "zigp_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "zigp_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
+    "zigp_get_engine": (C.c_int, [C.c_void_p]),
     "zigp_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "zigp_launch_count": (C.c_int64, [C.c_void_p]),
@@ -112,7 +114,13 @@ class Context:
     def launch_count(self) -> int:
         return int(lib().zigp_launch_count(self._h))
 
-    PROFILE_CLASSES = ("kgen", "gemm_tn", "point", "kgrad", "syrk", "mstage_fwd", "mstage_bwd", "reduce")
+    PROFILE_CLASSES = ("kgen", "gemm_tn", "point", "kgrad", "syrk", "mstage_fwd", "mstage_bwd", "reduce", "slice")
+
+    ENGINES = {"dmma": 0, "int8": 1}
+
+    def set_engine(self, engine):
+        """'dmma' (fp64 mma.sync) or 'int8' (fp64 emulated on the int8 tensor cores, csrc/ozaki.cuh)"""
+        self.call("zigp_set_engine", self.ENGINES[engine] if isinstance(engine, str) else int(engine))
 
     def set_profiling(self, on: bool):
         self.call("zigp_set_profiling", int(bool(on)))

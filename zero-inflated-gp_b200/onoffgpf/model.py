@@ -11,6 +11,7 @@ own shard of (X, Y); the per-shard packed accumulator is summed with ONE all-red
 every rank then runs the identical O(M^3) backward, so the KL term and its gradient enter exactly once."""
 from __future__ import annotations
 
+import os
 import pickle
 import time
 from typing import Optional
@@ -84,7 +85,7 @@ class OnOffSVGP(Parameterized):
     """
 
     def __init__(self, X, Y, kernf, kerng, likelihood, Zf, Zg, mean_function=None, minibatch_size=None, name="model",
-                 device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False):
+                 device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False, engine=None):
         if not torch.cuda.is_available():
             raise _cabi.ZigpError("OnOffSVGP needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _cabi.lib()  # fail loudly now if the extension is missing
@@ -134,6 +135,9 @@ class OnOffSVGP(Parameterized):
         if chunk_rows is None:
             chunk_rows = min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)
         self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, D, jitter, chunk_rows)
+        self.engine = engine or os.environ.get("ZIGP_ENGINE", "dmma")
+        self._ctx.set_engine(self.engine)
+        self._chunk_rows = int(chunk_rows)
         self.jitter = float(jitter)
         for p in self._theta_params():
             p.to(self.device)
@@ -328,7 +332,8 @@ class OnOffSVGP(Parameterized):
         self._Xb, self._Yb = self._X_dev, self._Y_dev
         rows = min(self.minibatch_size, self.num_data_local)
         self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, self.input_dim, self.jitter,
-                                  min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512))
+                                  getattr(self, "_chunk_rows", min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)))
+        self._ctx.set_engine(getattr(self, "engine", "dmma"))
         self._last_out = None
 
     # -- host-buffer entry (bench.py e2e; the call a non-torch binding would make) -----------------------------
