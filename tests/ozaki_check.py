@@ -55,5 +55,26 @@ def main():
             ms = timeit(eng, tri)
             print("tri %d %-16s %.3f ms  = %.1f TFLOP/s fp64-equivalent" % (tri, nm, ms, flop / ms * 1e-9), flush=True)
 
+def kscan():
+    """fixed per-tile overhead vs per-k-step cost: full products of 65536 x 1024 outputs with K = 128 ... 1024"""
+    dev = torch.device("cuda:0")
+    ctx = _cabi.Context(0, 64, 64, 1, 1e-6, 512)
+    rows, cols = 65536, 1024
+    st = torch.cuda.current_stream().cuda_stream
+    for K in (128, 256, 512, 1024):
+        In = torch.randn(rows, K, dtype=torch.float64, device=dev); W = torch.randn(cols, K, dtype=torch.float64, device=dev)
+        Out = torch.empty((rows, cols), dtype=torch.float64, device=dev)
+        ctx.call("zigp_debug_gemm", 1, In.data_ptr(), K, W.data_ptr(), K, Out.data_ptr(), cols, rows, cols, K, 0, None, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ctx.call("zigp_debug_gemm", 2, In.data_ptr(), K, W.data_ptr(), K, Out.data_ptr(), cols, rows, cols, K, 0, None, st)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("K %4d: %.3f ms  -> %.2f us per 128x64 tile (%d k-steps of 32)" % (K, ms, ms * 1e3 / (rows // 128 * cols // 64 / 148.0), K // 32), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "kscan":
+        kscan(); sys.exit(0)
     main()

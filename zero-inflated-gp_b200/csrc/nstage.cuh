@@ -163,7 +163,8 @@ struct KgradArgs {
     const double* X; long long n0; int nvalid, rows;
     const double* Z; int M, D, Mp;
     double* partial;     // [nslots][2 + 2*D][Mp]
-    double* Aw;          // out: gv[n] * A[n,m]  (row-scaled copy consumed by syrk_nt_f64), same ld
+    double* Aw;          // out: gv[n] * A[n,m]  (row-scaled copy consumed by syrk_nt_f64), same ld; null with the int8 engine
+    unsigned long long* cmaxA; unsigned long long* cmaxAw;   // int8 engine: per-column max |A|, max |gv A| over the chunk (bit patterns)
 };
 
 __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
     const int nr = min(KG_ROWS, p.nvalid - r0);
     if (nr <= 0) {                                     // padding rows of the chunk: Aw must still be defined (zero)
         const int nz = min(KG_ROWS, p.rows - r0);
-        for (int r = 0; r < nz; r++) p.Aw[(long long)(r0 + r) * p.ld + m] = 0.0;
+        if (p.Aw) for (int r = 0; r < nz; r++) p.Aw[(long long)(r0 + r) * p.ld + m] = 0.0;
         return;
     }
     for (int e = threadIdx.x; e < nr * p.D; e += 128) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
 #pragma unroll
     for (int d = 0; d < ZIGP_MAX_D; d++) { z[d] = (d < p.D && m < p.M) ? p.Z[m * p.D + d] : 0.0; s1[d] = 0.0; q[d] = 0.0; }
     const double bm = p.beta[m];
-    double s0 = 0.0, am = 0.0;
+    double s0 = 0.0, am = 0.0, mxa = 0.0, mxw = 0.0;
     const double* Kp = p.K + (long long)r0 * p.ld + m;
     const double* Yp = p.Y + (long long)r0 * p.ld + m;
     const double* Ap = p.A + (long long)r0 * p.ld + m;
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
 #pragma unroll 8
     for (int r = 0; r < nr; r++) {
         const double k = Kp[(long long)r * p.ld], yy = Yp[(long long)r * p.ld], aa = Ap[(long long)r * p.ld];
-        Awp[(long long)r * p.ld] = sgv[r] * aa;
+        if (p.Aw) Awp[(long long)r * p.ld] = sgv[r] * aa;
+        mxa = fmax(mxa, fabs(aa)); mxw = fmax(mxw, fabs(sgv[r] * aa));
         const double G = (sgm[r] * bm - 2.0 * sgv[r] * yy) * k;
         s0 += G;
         am = fma(sgm[r], aa, am);
@@ -201,7 +203,11 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
             if (d < p.D) { double df = sx[r][d] - z[d]; s1[d] = fma(G, df, s1[d]); q[d] = fma(G * df, df, q[d]); }
         }
     }
-    for (int r = nr; r < min(KG_ROWS, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
+    if (p.Aw) for (int r = nr; r < min(KG_ROWS, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
+    if (p.cmaxA) {
+        atomicMax(p.cmaxA + m, (unsigned long long)__double_as_longlong(mxa));
+        atomicMax(p.cmaxAw + m, (unsigned long long)__double_as_longlong(mxw));
+    }
     double* out = p.partial + (long long)blockIdx.y * (2 + 2 * p.D) * p.Mp + m;
     out[0] += s0;
     out[(long long)p.Mp] += am;

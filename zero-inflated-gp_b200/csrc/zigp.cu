@@ -395,6 +395,10 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             KgradArgs k{};
             k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
             k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows; k.Aw = L.Vb; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
+            if (c->engine == 1) {          // the rank update slices A and gv*A itself: no Aw copy, but the column maxima of both
+                k.Aw = nullptr; k.cmaxA = c->oz_colmax; k.cmaxAw = c->oz_colmax + L.Mp;
+                CK(cudaMemsetAsync(c->oz_colmax, 0, (size_t)2 * L.Mp * sizeof(unsigned long long), st));
+            }
             dim3 gg(L.Mp / 128, (rows + KG_ROWS - 1) / KG_ROWS);
             {
                 ProfScope ps(c, PC_KGRAD, st);
@@ -405,9 +409,9 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
                 // E += Aw^T A on the int8 engine: the operands are the columns of Aw and A (k index = point), sliced transposed
                 {
                     ProfScope ps(c, PC_SLICE, st);
-                    CK(oz::launch_slice_cols(L.Vb, L.Mp, rows, L.Mp, c->oz_colmax, c->oz_colAw, (long long)L.Mp * rows, c->oz_csAw, st));
-                    CK(oz::launch_slice_cols(L.Ab, L.Mp, rows, L.Mp, c->oz_colmax + L.Mp, c->oz_colA, (long long)L.Mp * rows, c->oz_csA, st));
-                    c->launches += 4;
+                    CK(oz::launch_slice_cols_pair(L.Ab, L.Mp, rows, L.Mp, L.gv, c->oz_colmax, c->oz_colmax + L.Mp, c->oz_colA, c->oz_colAw,
+                                                  (long long)L.Mp * rows, c->oz_csA, c->oz_csAw, st));
+                    c->launches++;
                 }
                 oz::OzOperand A{c->oz_colAw, rows, L.Mp, (long long)L.Mp * rows, c->oz_csAw};
                 oz::OzOperand B{c->oz_colA, rows, L.Mp, (long long)L.Mp * rows, c->oz_csA};
