@@ -49,7 +49,6 @@ __device__ __forceinline__ void slice8(double t, int (&d)[NSL]) {
         d[4 + i] = lo; h2 = (h2 - lo) >> 7;
     }
     d[4] = h2;                                          // |.| <= 64
-    h1 += 0;                                            // (no carry: h2's top digit stays within [-64, 64] because |v2| <= 2^27)
 #pragma unroll
     for (int i = 3; i >= 1; i--) {
         const int lo = ((h1 + 64) & 127) - 64;
@@ -156,7 +155,7 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restric
 struct OzArgs {
     const double* rscale;   // [rows]  2^e of the In rows
     const double* cscale;   // [cols]  2^f of the W rows (= output columns)
-    double* Out; long long ldo;
+    double* Out; long long ldo;                 // Out may be null: statistics only
     const double* Zin; long long ldz;
     double alpha, beta;
     int rows, cols, kdim, tri;                  // TriMode as in gemm_f64.cuh (k index space == column index space)
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     const double2 z = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j);
                     v0 += g.beta * z.x; v1 += g.beta * z.y;
                 }
-                *reinterpret_cast<double2*>(Out + (long long)r * g.ldo + c + j) = make_double2(v0, v1);
+                if (g.Out) *reinterpret_cast<double2*>(Out + (long long)r * g.ldo + c + j) = make_double2(v0, v1);
                 if (g.OutSq) *reinterpret_cast<double2*>(g.OutSq + (long long)r * g.ldo + c + j) = make_double2(v0 * v0, v1 * v1);
                 if (g.stat_sq) {
                     ssq = fma(v0, v0, ssq); ssq = fma(v1, v1, ssq);
@@ -519,7 +518,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
                         const double2 z = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j);
                         v0 += g.beta * z.x; v1 += g.beta * z.y;
                     }
-                    *reinterpret_cast<double2*>(Out + (long long)r * g.ldo + c + j) = make_double2(v0, v1);
+                    if (g.Out) *reinterpret_cast<double2*>(Out + (long long)r * g.ldo + c + j) = make_double2(v0, v1);
                     if (g.OutSq) *reinterpret_cast<double2*>(g.OutSq + (long long)r * g.ldo + c + j) = make_double2(v0 * v0, v1 * v1);
                     if (g.stat_sq) {
                         ssq = fma(v0, v0, ssq); ssq = fma(v1, v1, ssq);

@@ -37,9 +37,10 @@ struct Latent {
     int nsplit = 1;
     // accumulator views
     double *accE = nullptr, *accV = nullptr;
-    // int8 engine: slice planes + row scales of the four triangular factors (same order as ozW_src)
-    int8_t* ozW[4] = {nullptr, nullptr, nullptr, nullptr};
-    double* ozWs[4] = {nullptr, nullptr, nullptr, nullptr};
+    // int8 engine: slice planes + row scales of the factors T (lower), R (upper), G = T^T (I - R^T R) (full)
+    int8_t* ozW[3] = {nullptr, nullptr, nullptr};
+    double* ozWs[3] = {nullptr, nullptr, nullptr};
+    double* Gf = nullptr;
     int nsplit_oz = 4;
 };
 
@@ -194,35 +195,7 @@ int dalloc(zigp_ctx* c, double** p, long long n) {
 #define ZIGP_STAGES 2
 #endif
 
-// int8 engine: is g.W one of the pre-sliced triangular factors?
-bool oz_lookup(zigp_ctx* c, const double* W, int8_t** planes, double** scale, int* Mp) {
-    for (int l = 0; l < 2; l++) {
-        Latent& L = c->lat[l];
-        const double* src[4] = {L.T, L.R, L.Rt, L.Tt};
-        for (int i = 0; i < 4; i++)
-            if (W == src[i] && L.ozW[i]) { *planes = L.ozW[i]; *scale = L.ozWs[i]; *Mp = L.Mp; return true; }
-    }
-    return false;
-}
-
 int gemmN(zigp_ctx* c, const GemmArgs& g, cudaStream_t st) {
-    int8_t* wp = nullptr; double* ws = nullptr; int Mp = 0;
-    if (c->engine == 1 && !c->kron && g.rows % oz::OBM == 0 && g.cols % oz::OBN == 0 && g.kdim % 128 == 0 && oz_lookup(c, g.W, &wp, &ws, &Mp)) {
-        {
-            ProfScope ps(c, PC_SLICE, st);
-            CK(oz::launch_slice_rows(g.In, g.ldi, g.rows, g.kdim, nullptr, c->oz_in, (long long)g.rows * g.kdim, c->oz_rs, st));
-            c->launches++;
-        }
-        oz::OzOperand A{c->oz_in, g.kdim, g.rows, (long long)g.rows * g.kdim, c->oz_rs};
-        oz::OzOperand B{wp, Mp, Mp, (long long)Mp * Mp, ws};
-        oz::OzArgs a{};
-        a.Out = g.Out; a.ldo = g.ldo; a.Zin = g.Zin; a.ldz = g.ldz; a.alpha = g.alpha; a.beta = g.beta; a.rows = g.rows; a.cols = g.cols; a.kdim = g.kdim;
-        a.tri = g.tri; a.stat_sq = g.stat_sq; a.stat_dot = g.stat_dot; a.dotvec = g.dotvec; a.OutSq = g.OutSq; a.nsplit = 1;
-        ProfScope ps(c, PC_GEMM, st);
-        CK(oz::launch_ozaki_gemm(A, B, a, st));
-        c->launches++;
-        return 0;
-    }
     ProfScope ps(c, PC_GEMM, st);
     CK((launch_gemm_tn<ZIGP_BM, ZIGP_BN, ZIGP_WM, ZIGP_WN, ZIGP_STAGES, ZIGP_MINB>(g, st)));
     c->launches++;
@@ -317,12 +290,37 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
     kl_kernel<<<1, 256, 0, st>>>(L.aw, L.s, L.dK, L.Lb, M, Mp, L.kl);
     LAUNCHED();
     if (c->engine == 1) {
-        const double* src[4] = {L.T, L.R, L.Rt, L.Tt};
-        for (int i = 0; i < 4; i++) {
+        // int8 engine: the backward product Y_n = T^T (I - R^T R) A_n is ONE full contraction with the explicit factor
+        // G = T^T (I - P), P = R^T R (instead of V = A - R^T RA followed by Y = T^T V): two operand slicings per chunk
+        // (K and A) instead of four, and RA / V are never written.
+        RUN(gemmM(c, L.Rt, Mp, L.Rt, Mp, L.P, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));                 // P = R^T R (symmetric)
+        RUN(gemmM(c, L.Tt, Mp, L.P, Mp, L.Gf, Mp, L.Tt, Mp, -1.0, 1.0, Mp, Mp, Mp, st));                  // G = T^T - T^T P
+        const double* src[3] = {L.T, L.R, L.Gf};
+        for (int i = 0; i < 3; i++) {
             CK(oz::launch_slice_rows(src[i], Mp, Mp, Mp, nullptr, L.ozW[i], (long long)Mp * Mp, L.ozWs[i], st));
             c->launches++;
         }
     }
+    return 0;
+}
+
+// int8 engine: one contraction of the chunk's sliced row operand (c->oz_in / c->oz_rs) with pre-sliced factor `wi` of the latent
+int oz_product(zigp_ctx* c, Latent& L, int wi, int rows, int tri, double* Out, double* stat_sq, double* stat_dot, const double* dotvec, cudaStream_t st) {
+    const int Mp = L.Mp;
+    oz::OzOperand A{c->oz_in, Mp, rows, (long long)rows * Mp, c->oz_rs};
+    oz::OzOperand B{L.ozW[wi], Mp, Mp, (long long)Mp * Mp, L.ozWs[wi]};
+    oz::OzArgs a{};
+    a.Out = Out; a.ldo = Mp; a.alpha = 1.0; a.beta = 0.0; a.rows = rows; a.cols = Mp; a.kdim = Mp; a.tri = tri;
+    a.stat_sq = stat_sq; a.stat_dot = stat_dot; a.dotvec = dotvec; a.nsplit = 1;
+    ProfScope ps(c, PC_GEMM, st);
+    CK(oz::launch_ozaki_gemm(A, B, a, st));
+    c->launches++;
+    return 0;
+}
+int oz_slice_in(zigp_ctx* c, const double* X, int rows, int Mp, cudaStream_t st) {
+    ProfScope ps(c, PC_SLICE, st);
+    CK(oz::launch_slice_rows(X, Mp, rows, Mp, nullptr, c->oz_in, (long long)rows * Mp, c->oz_rs, st));
+    c->launches++;
     return 0;
 }
 
@@ -335,6 +333,14 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
         ProfScope ps(c, PC_KGEN, st);
         kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, c->D, 0);
         LAUNCHED();
+    }
+    if (c->engine == 1 && rows % oz::OBM == 0) {
+        RUN(oz_slice_in(c, L.Kb, rows, Mp, st));
+        RUN(oz_product(c, L, 0, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, st));               // A = K T^T, |A|^2, A.alpha_w
+        RUN(oz_slice_in(c, L.Ab, rows, Mp, st));
+        RUN(oz_product(c, L, 1, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, st));       // |R A|^2 only: RA is never stored
+        if (need_bwd) RUN(oz_product(c, L, 2, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, st));   // Y = G A
+        return 0;
     }
     GemmArgs g{};
     g.rows = rows; g.cols = Mp; g.kdim = Mp; g.alpha = 1.0; g.beta = 0.0;
@@ -900,10 +906,11 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
         DA(c->oz_rs, chunk); DA(c->oz_csA, Mpmax); DA(c->oz_csAw, Mpmax);
         for (int l = 0; l < 2; l++) {
             Latent& L = c->lat[l];
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < 3; i++) {
                 RUN(balloc((void**)&L.ozW[i], (size_t)oz::NSL * L.Mp * L.Mp));
                 DA(L.ozWs[i], L.Mp);
             }
+            DA(L.Gf, (long long)L.Mp * L.Mp);
         }
     }
     c->engine = engine;
