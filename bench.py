@@ -294,6 +294,12 @@ def run_ours(a):
     # M x M triangular factor: M^2 flop per point (each of the six products per latent is M^2 flop)
     flops_per_launch = float(M) * M * (n_loc / max(1, gemm_n / 8))      # 8 launches per chunk (4 per latent)
     achieved = flops_per_launch / (gemm_ms / max(1, gemm_n) * 1e-3) * 1e-12 if gemm_n else 0.0
+    int8 = (not kron) and getattr(m, "engine", "dmma") == "int8"
+    if int8:
+        # int8 engine: per chunk and latent three launches of ozaki_gemm_kernel_v2 (A = K T^T lower, |R A|^2 upper, Y = G A full) =
+        # 4 M^2 fp64-equivalent flop per point per latent; each is 36 int8 slice products (8 x 7-bit slices, weights <= 7)
+        gflop = 2.0 * 4.0 * float(M) * M * n_loc
+        achieved = gflop / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else 0.0
     if kron:
         # per point and latent the contraction class runs 8 triangular factor products (Ms^2 or Mt^2 flop each) and 4 full
         # Ms x Mt products (2 Ms Mt flop each); the rate is averaged over all of them
@@ -327,18 +333,43 @@ def run_ours(a):
                     "note": "zigp_set_data_host + accumulate/finish + D2H of the packed ELBO/gradient, pinned host buffers"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic_per_launch(M, ctx_chunk_rows(m)) if not kron else None,
-                         "peak_source": "cuBLAS DGEMM 4096^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue ceiling 37.1 TFLOP/s, profiles/microbench)",
+            "roofline": roofline_head(int8, kron, achieved, peak_tf, M, m) | {
                          "whole_step_algorithmic_tflops": alg * world / (ms_step * 1e-3) * 1e-12 if world == 1 else None,
                          "whole_step_frac": (alg / (ms_step * 1e-3) * 1e-12 / peak_tf) if (world == 1 and peak_tf) else None,
                          "kernel_share_of_step": gemm_ms / total_prof if total_prof else None,
                          "class_ms": {k: round(v[0], 3) for k, v in prof.items()}, "class_launches": {k: int(v[1]) for k, v in prof.items()}},
+            "engine": getattr(m, "engine", "dmma"),
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def roofline_head(int8, kron, achieved, dgemm_tf, M, m):
+    """the roofline block of the dominant kernel.  DMMA engine: fp64 flop/s against the cuBLAS DGEMM rate measured in this run.
+    int8 engine: the kernel executes 36 int8 slice products per fp64-equivalent product, so `achieved` is the executed int8
+    rate (TOP/s) against the int8 tensor peak, taken as 2 x the MEASURED bf16 rate (MEASURED_PEAKS.json has no int8 entry; the
+    nominal int8 : bf16 ratio of B200 is 2); the fp64-equivalent rate and the DGEMM rate it replaces are given beside it."""
+    if int8:
+        mp = measured_peaks()
+        bf16 = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
+        src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a long, power-capped step)" if mp else "2 x 1400 (fallback: no MEASURED_PEAKS.json)"
+        peak = 2.0 * (bf16 if bf16 else 1400.0)
+        return {"bound": "tensor", "kernel": "ozaki_gemm_kernel_v2<2> (tcgen05.mma kind::i8, 128x64 tiles, 8x7-bit slices = 36 slice products, TMA multicast in 2-CTA clusters, persistent)",
+                "achieved": achieved * 36.0, "peak": peak, "unit": "TOP/s", "frac": achieved * 36.0 / peak, "traffic": None,
+                "peak_source": src, "fp64_equivalent_tflops": achieved, "dgemm_tflops_measured": dgemm_tf,
+                "fp64_equivalent_over_dgemm": achieved / dgemm_tf if dgemm_tf else None}
+    return {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": dgemm_tf,
+            "unit": "TFLOP/s", "frac": achieved / dgemm_tf if dgemm_tf else None, "traffic": traffic_per_launch(M, ctx_chunk_rows(m)) if not kron else None,
+            "peak_source": "cuBLAS DGEMM 4096^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue ceiling 37.1 TFLOP/s, profiles/microbench)"}
 
 
 def ctx_chunk_rows(m):

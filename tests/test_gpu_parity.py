@@ -57,6 +57,13 @@ def check_against(out, gc, gf, e, dt, kl, g, gfree, tol_grad):
             assert np.linalg.norm(a - b) <= tol_grad * np.linalg.norm(b) + 1e-12 * full, (tag + k, relnorm(a, b))
 
 
+@pytest.fixture(params=["int8", "dmma"], autouse=True)
+def engine(request, monkeypatch):
+    """every parity test runs on both contraction engines: fp64 emulated on the int8 tensor cores (tcgen05, the default) and DMMA"""
+    monkeypatch.setenv("ZIGP_ENGINE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small", "ragged"])
 def test_golden_synthetic(name):
     z = np.load(os.path.join(G, "synth_%s.npz" % name))

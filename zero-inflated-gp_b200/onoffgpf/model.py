@@ -81,7 +81,7 @@ class OnOffSVGP(Parameterized):
     - X is a data matrix, size N x D; Y is N x 1
     - kernf, kerng are RBF kernel objects for the f (magnitude) and g (on/off) processes
     - Zf, Zg are inducing point locations, Mf x D and Mg x D
-    Extra keyword arguments (not in the reference): device, jitter, chunk_rows, distributed.
+    Extra keyword arguments (not in the reference): device, jitter, chunk_rows, distributed, engine ('int8' | 'dmma').
     """
 
     def __init__(self, X, Y, kernf, kerng, likelihood, Zf, Zg, mean_function=None, minibatch_size=None, name="model",
@@ -135,7 +135,8 @@ class OnOffSVGP(Parameterized):
         if chunk_rows is None:
             chunk_rows = min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)
         self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, D, jitter, chunk_rows)
-        self.engine = engine or os.environ.get("ZIGP_ENGINE", "dmma")
+        # contraction engine: "int8" = fp64 emulated on the int8 tensor cores (csrc/ozaki.cuh, the default), "dmma" = fp64 mma.sync
+        self.engine = engine or os.environ.get("ZIGP_ENGINE", "int8")
         self._ctx.set_engine(self.engine)
         self._chunk_rows = int(chunk_rows)
         self.jitter = float(jitter)
@@ -333,7 +334,7 @@ class OnOffSVGP(Parameterized):
         rows = min(self.minibatch_size, self.num_data_local)
         self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, self.input_dim, self.jitter,
                                   getattr(self, "_chunk_rows", min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)))
-        self._ctx.set_engine(getattr(self, "engine", "dmma"))
+        self._ctx.set_engine(getattr(self, "engine", "int8"))
         self._last_out = None
 
     # -- host-buffer entry (bench.py e2e; the call a non-torch binding would make) -----------------------------
