@@ -68,7 +68,7 @@ int kron_chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X,
         dim3 gk(F.Mp / 32, rows / 64);
         {
             ProfScope ps(c, PC_KGEN, st);
-            kgen_kernel<<<gk, 256, 0, st>>>(X, theta + F.off_Z, theta + F.off_ell, theta + F.off_var, n0, nvalid, rows, F.M, F.D, F.Mp, F.Kb, xstride, F.xoff);
+            kgen_kernel<<<gk, 128, 0, st>>>(X, theta + F.off_Z, theta + F.off_ell, theta + F.off_var, n0, nvalid, rows, F.M, F.D, F.Mp, F.Kb, xstride, F.xoff);
             LAUNCHED();
         }
         RUN(kron_gemm(c, F.Kb, F.Mp, F.T, F.Mp, F.Ab, F.Mp, rows, F.Mp, F.Mp, TRI_LOWER, F.sq, nullptr, st));                      // a = T k

@@ -9,13 +9,15 @@ namespace zigp {
 // x_n = X[n*xstride + xoff .. + D): the dense path passes (D, 0); a Kronecker factor reads its own column group
 // (scripts/onoff.py:243-250).
 // Point-major (m contiguous) so that every later contraction reads k-contiguous operands.  (onofftf/main.py:53-57)
-__global__ void __launch_bounds__(256) kgen_kernel(const double* __restrict__ X, const double* __restrict__ Z,
+__global__ void __launch_bounds__(128) kgen_kernel(const double* __restrict__ X, const double* __restrict__ Z,
                                                    const double* __restrict__ ell, const double* __restrict__ var, long long n0,
                                                    int nvalid, int rows, int M, int D, int Mp, double* __restrict__ K,
                                                    int xstride, int xoff) {
-    __shared__ double sx[8][ZIGP_MAX_D];
+    // 128 threads (32 columns x 4 rows per pass, 64 rows per block): small enough in registers to share an SM with a
+    // persistent int8 contraction CTA of the other latent's stream
+    __shared__ double sx[4][ZIGP_MAX_D];
     const int m = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int rl = threadIdx.x >> 5;                 // 8 rows per pass
+    const int rl = threadIdx.x >> 5;                 // 4 rows per pass
     double z[ZIGP_MAX_D], il[ZIGP_MAX_D];
 #pragma unroll
     for (int d = 0; d < ZIGP_MAX_D; d++) {
@@ -24,7 +26,7 @@ __global__ void __launch_bounds__(256) kgen_kernel(const double* __restrict__ X,
     }
     const double v = var[0];
     const int rbeg = blockIdx.y * 64;
-    for (int rr = rbeg; rr < rbeg + 64; rr += 8) {
+    for (int rr = rbeg; rr < rbeg + 64; rr += 4) {
         const int r = rr + rl;
         __syncthreads();
         if ((threadIdx.x & 31) < D && r < nvalid) sx[rl][threadIdx.x & 31] = X[(n0 + r) * xstride + xoff + (threadIdx.x & 31)];
@@ -167,7 +169,7 @@ struct KgradArgs {
     unsigned long long* cmaxA; unsigned long long* cmaxAw;   // int8 engine: per-column max |A|, max |gv A| over the chunk (bit patterns)
 };
 
-__global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
+__global__ void __launch_bounds__(128, 6) kgrad_kernel(const KgradArgs p) {
     __shared__ double sx[KG_ROWS][ZIGP_MAX_D];
     __shared__ double sgm[KG_ROWS], sgv[KG_ROWS];
     const int m = blockIdx.x * 128 + threadIdx.x;

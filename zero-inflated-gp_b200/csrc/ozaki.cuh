@@ -21,40 +21,49 @@
 namespace zigp {
 namespace oz {
 
-constexpr int NSL = 8;                       // slices per operand
+#ifndef ZIGP_OZ_SBITS
+#define ZIGP_OZ_SBITS 7
+#endif
+// Slice width.  8: seven signed 8-bit slices (digits in [-128, 127], |t| < 1/4 so that the leading digit fits), 28 slice products;
+// 7: eight 7-bit slices (digits in [-64, 64], |t| < 1/2), 36 slice products.  Both carry 55-56 bits below the row scale; int32
+// accumulation is exact for contraction lengths up to 2^31 / (2^(2 SBITS) NSL): 18724 (8-bit) / 65536 (7-bit) per accumulation.
+constexpr int SBITS = ZIGP_OZ_SBITS;
+constexpr int NSL = 56 / SBITS;               // slices per operand (7 or 8)
+constexpr int NPA = NSL;                      // slice planes per shared-memory stage of the row operand
+constexpr int EOFF = (SBITS == 8) ? 3 : 2;    // exponent offset: |x| 2^-e < 2^(1 - EOFF)
+constexpr double INVB = (SBITS == 8) ? 1.0 / 256.0 : 1.0 / 128.0;
+constexpr double INVB2 = INVB * INVB;         // product scale 2^(-2 SBITS)
+constexpr int MAX_ACC_K = (SBITS == 8) ? 16384 : 32768;   // longest contraction accumulated in one int32 pass
 #ifndef ZIGP_OZ_SW
 #define ZIGP_OZ_SW 32
 #endif
 constexpr int OBM = 128, OBN = 64;            // tile rows, tile columns
 constexpr int UK = 32;                        // k depth of one tcgen05.mma kind::i8 (bytes == int8 elements)
 constexpr int OBK = ZIGP_OZ_SW;               // k bytes per pipeline stage == TMA swizzle span (32 / 64 / 128)
-constexpr int OSTAGES = 128 / OBK;            // 192 KB of stages either way
-constexpr int A_STAGE = NSL * OBM * OBK;
+constexpr int OSTAGES = (SBITS == 8 ? 5 : 4) * 32 / OBK;   // 5 x 42 KB (seven slices) or 4 x 48 KB (eight slices) at the 32-byte span
+constexpr int A_STAGE = NPA * OBM * OBK;
 constexpr int B_STAGE = NSL * OBN * OBK;
 constexpr int OZ_THREADS = 192;               // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr size_t OZ_SMEM = (size_t)OSTAGES * (A_STAGE + B_STAGE) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ---- slicing ------------------------------------------------------------------------------------------------------------
-// 56 fractional bits of t (|t| < 1/2) as 8 balanced base-128 digits, most significant first:  t ~= sum_p d[p] 2^(-7(p+1)),
-// |d[p]| <= 64.  Two double -> int32 roundings (28 bits each) and integer digit extraction: the per-slice F2I / I2F chain of the
-// obvious loop is fp64-conversion bound (profiles: 0.27 ms per 65536 x 1024 matrix against 0.17 ms of HBM time).
+// 56 fractional bits of t (|t| < 2^(1-EOFF)) as NSL balanced base-2^SBITS digits, most significant first:
+//     t ~= sum_p d[p] 2^(-SBITS (p+1)),   d[p>0] in [-2^(SBITS-1), 2^(SBITS-1) - 1],  |d[0]| <= 2^(SBITS-2) + 1.
+// Two double -> int32 roundings (28 bits each) and integer digit extraction: the per-slice F2I / I2F chain of the obvious loop
+// is fp64-conversion bound.
 __device__ __forceinline__ void slice8(double t, int (&d)[NSL]) {
     const double v1 = t * 268435456.0;                 // 2^28, exact
-    int h1 = __double2int_rn(v1);
+    const int h1 = __double2int_rn(v1);
     const double v2 = (v1 - (double)h1) * 268435456.0; // exact remainder, |.| <= 2^27
-    int h2 = __double2int_rn(v2);
+    const int h2 = __double2int_rn(v2);
+    long long V = ((long long)h1 << 28) + (long long)h2;    // round(t 2^56)
+    constexpr long long HALF = 1LL << (SBITS - 1), MASK = (1LL << SBITS) - 1;
 #pragma unroll
-    for (int i = 3; i >= 1; i--) {
-        const int lo = ((h2 + 64) & 127) - 64;         // balanced digit in [-64, 63]
-        d[4 + i] = lo; h2 = (h2 - lo) >> 7;
+    for (int i = NSL - 1; i >= 1; i--) {
+        const long long lo = ((V + HALF) & MASK) - HALF;
+        d[i] = (int)lo; V = (V - lo) >> SBITS;
     }
-    d[4] = h2;                                          // |.| <= 64
-#pragma unroll
-    for (int i = 3; i >= 1; i--) {
-        const int lo = ((h1 + 64) & 127) - 64;
-        d[i] = lo; h1 = (h1 - lo) >> 7;
-    }
-    d[0] = h1;
+    d[0] = (int)V;
 }
 
 // planes[p][r][k] = X_p of row r (k contiguous, plane stride in bytes), scale[r] = 2^e.  One warp per row; K % 128 == 0.
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     mx *= fabs(wgt);
     int e = 0;
-    if (mx > 0.0) e = ilogb(mx) + 2;            // |x| 2^-e < 1/2
+    if (mx > 0.0) e = ilogb(mx) + EOFF;
     const double inv = scalbn(1.0, -e) * wgt;   // exact (power of two) when wgt == 1; with a weight the product x*wgt is rounded once
     if (lane == 0) scale[r] = scalbn(1.0, e);
     int8_t* out = planes + (long long)r * K;
@@ -109,28 +118,29 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
     }
 }
 
-// Pass 2: slice a 128 (n) x 32 (columns) tile per block and write it transposed.  n % 128 == 0, m % 32 == 0.
+// Pass 2: slice a 64 (n) x 32 (columns) tile per block and write it transposed.  n % 64 == 0, m % 32 == 0.
 // With rowweight the kernel also emits the slices of diag(rowweight) X (planes2 / scale2, maxima colmax2) from the same read.
-__global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restrict__ X, long long ld, int n, int m,
+__global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restrict__ X, long long ld, int n, int m,
                                                           const unsigned long long* __restrict__ colmax, int8_t* __restrict__ planes,
                                                           long long plane_stride, double* __restrict__ scale,
                                                           const double* __restrict__ rowweight, const unsigned long long* __restrict__ colmax2,
                                                           int8_t* __restrict__ planes2, double* __restrict__ scale2) {
-    __shared__ double tile[128][33];
-    __shared__ double sw[128];
-    const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 128;
-    for (int e = threadIdx.x; e < 128 * 32; e += 256) {
+    // 64 (n) x 32 (columns) tile, 128 threads, 17 KB of shared memory: fits beside a persistent contraction CTA
+    __shared__ double tile[64][33];
+    __shared__ double sw[64];
+    const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 64;
+    for (int e = threadIdx.x; e < 64 * 32; e += 128) {
         const int r = e >> 5, cc = e & 31;
         tile[r][cc] = X[(long long)(n0 + r) * ld + c0 + cc];
     }
-    if (rowweight && threadIdx.x < 128) sw[threadIdx.x] = rowweight[n0 + threadIdx.x];
+    if (rowweight && threadIdx.x < 64) sw[threadIdx.x] = rowweight[n0 + threadIdx.x];
     __syncthreads();
-    // thread -> (column cc, 16 consecutive n): 32 columns x 8 groups of 16
-    const int cc = threadIdx.x >> 3, grp = threadIdx.x & 7;
+    // thread -> (column cc, 16 consecutive n): 32 columns x 4 groups of 16
+    const int cc = threadIdx.x >> 2, grp = threadIdx.x & 3;
     for (int pass = 0; pass < (rowweight ? 2 : 1); pass++) {
         const double mx = __longlong_as_double((long long)(pass ? colmax2 : colmax)[c0 + cc]);
         int e = 0;
-        if (mx > 0.0) e = ilogb(mx) + 2;
+        if (mx > 0.0) e = ilogb(mx) + EOFF;
         const double inv = scalbn(1.0, -e);
         if (blockIdx.y == 0 && grp == 0) (pass ? scale2 : scale)[c0 + cc] = scalbn(1.0, e);
         int8_t* out = (pass ? planes2 : planes) + (long long)(c0 + cc) * n + n0 + grp * 16;
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         const int r = row0 + rl;
         tc05::mbar_wait(tmem_full, 0);
         tc05::fence_after_thread_sync();
-        const double rs = g.rscale[r] * (1.0 / 16384.0);          // 2^e * 2^-14
+        const double rs = g.rscale[r] * INVB2;
         double* Out = g.Out + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0);
         const double* Zin = g.Zin ? g.Zin + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0) : nullptr;
         double ssq = 0.0, sdt = 0.0;
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 tc05::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(w * OBN + c0), v);
                 tc05::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], 1.0 / 128.0, (double)(int)v[j]);
+                for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], INVB, (double)(int)v[j]);
             }
             const int c = col0 + c0;
 #pragma unroll
@@ -328,7 +338,7 @@ __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
 }
 
 template <int CL>
-__global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                                                                       const __grid_constant__ CUtensorMap mapB, const OzArgs g) {
     extern __shared__ uint8_t oz_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
     const uint32_t cid = (CL > 1) ? tc05::cluster_id_x() : blockIdx.x;
     const uint32_t ncl = (CL > 1) ? tc05::num_clusters_x() : gridDim.x;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
-    constexpr int PL = NSL / CL;            // slice planes of the row operand fetched by each CTA
+    constexpr int PL = (NSL + CL - 1) / CL; // slice planes of the row operand fetched by each CTA (mapA: PL planes; the last rank takes the remainder through mapA2)
 
     const int ntr = g.rows / OBM, ntc = g.cols / OBN, ntcg = ntc / CL;
     // rank-update mode enumerates only the cluster-tiles that touch the lower triangle (row tile tr owns tcg <= (128 tr + 127) / (CL 64))
@@ -355,6 +365,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
 
     if (warp == 0 && lane == 0) {
         tc05::prefetch_tensormap(&mapA);
+        tc05::prefetch_tensormap(&mapA2);
         tc05::prefetch_tensormap(&mapB);
     }
     if (warp == 1) {
@@ -414,8 +425,9 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
                     tc05::mbar_wait(&empty[s], ph ^ 1u);
                     tc05::mbar_arrive_expect_tx(&full[s], A_STAGE + (active ? B_STAGE : 0));
                     uint8_t* dstA = sA + (size_t)s * A_STAGE + (size_t)rank * PL * OBM * OBK;
-                    if (CL > 1) tc05::tma_load_3d_mcast(dstA, &mapA, &full[s], k0, row0, (int)rank * PL, CMASK);
-                    else tc05::tma_load_3d(dstA, &mapA, &full[s], k0, row0, 0);
+                    const CUtensorMap* mA = (NSL % CL != 0 && rank == CL - 1) ? &mapA2 : &mapA;
+                    if (CL > 1) tc05::tma_load_3d_mcast(dstA, mA, &full[s], k0, row0, (int)rank * PL, CMASK);
+                    else tc05::tma_load_3d(dstA, mA, &full[s], k0, row0, 0);
                     if (active) tc05::tma_load_3d(sB + (size_t)s * B_STAGE, &mapB, &full[s], k0, col0, 0);
                 }
             }
@@ -481,10 +493,17 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
             for (int ch = 0; ch < 2; ch++) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) acc[ch][j] = 0.0;
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32 + ch * 16);
+                if (NSL & 1) {                              // odd slice count: the top weight alone
+                    uint32_t v0[16];
+                    tc05::tmem_ld16(ta + (uint32_t)((NSL - 1) * OBN), v0);
+                    tc05::tmem_ld_wait();
 #pragma unroll
-                for (int w = NSL - 1; w >= 0; w -= 2) {
+                    for (int j = 0; j < 16; j++) acc[ch][j] = __hiloint2double(0x43300000, (int)(v0[j] ^ 0x80000000u)) - 4503601774854144.0;
+                }
+#pragma unroll
+                for (int w = (NSL & ~1) - 1; w >= 0; w -= 2) {
                     uint32_t v0[16], v1[16];
-                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32 + ch * 16);
                     tc05::tmem_ld16(ta + (uint32_t)(w * OBN), v0);
                     tc05::tmem_ld16(ta + (uint32_t)((w - 1) * OBN), v1);
                     tc05::tmem_ld_wait();
@@ -493,7 +512,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
                         // int32 -> double through the 2^52 + 2^31 bias: exact, one DADD instead of an I2F
                         const double d0 = __hiloint2double(0x43300000, (int)(v0[j] ^ 0x80000000u)) - 4503601774854144.0;
                         const double d1 = __hiloint2double(0x43300000, (int)(v1[j] ^ 0x80000000u)) - 4503601774854144.0;
-                        acc[ch][j] = fma(fma(acc[ch][j], 1.0 / 128.0, d0), 1.0 / 128.0, d1);
+                        acc[ch][j] = fma(fma(acc[ch][j], INVB, d0), INVB, d1);
                     }
                 }
             }
@@ -503,7 +522,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
             if (lane == 0) tc05::mbar_arrive(tmem_empty);
             ti++;
 
-            const double rs = g.rscale[r] * (1.0 / 16384.0);
+            const double rs = g.rscale[r] * INVB2;
             double* Out = g.Out + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0);
             const double* Zin = g.Zin ? g.Zin + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0) : nullptr;
             double ssq = 0.0, sdt = 0.0;
@@ -591,7 +610,7 @@ inline cudaError_t launch_ozaki_gemm_v1(const OzOperand& A, const OzOperand& B, 
         attr_done = true;
     }
     CUtensorMap ma, mb;
-    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, OBM)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, OBM, NPA)) return cudaErrorInvalidValue;
     if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, OBN)) return cudaErrorInvalidValue;
     g.rscale = A.scale; g.cscale = B.scale;
     if (g.nsplit < 1) g.nsplit = 1;
@@ -613,8 +632,10 @@ inline cudaError_t launch_ozaki_gemm_v2(const OzOperand& A, const OzOperand& B, 
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
         attr_done = true;
     }
-    CUtensorMap ma, mb;
-    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, OBM, NSL / CL)) return cudaErrorInvalidValue;
+    CUtensorMap ma, ma2, mb;
+    constexpr int PL = (NSL + CL - 1) / CL, PL2 = NSL - PL * (CL - 1);
+    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, OBM, PL)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&ma2, A.planes, A.K, A.nrows, A.plane_stride, OBM, PL2 > 0 ? PL2 : PL)) return cudaErrorInvalidValue;
     if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, OBN)) return cudaErrorInvalidValue;
     g.rscale = A.scale; g.cscale = B.scale;
     if (g.nsplit < 1) g.nsplit = 1;
@@ -630,7 +651,7 @@ inline cudaError_t launch_ozaki_gemm_v2(const OzOperand& A, const OzOperand& B, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ma, mb, g);
+    return cudaLaunchKernelEx(&cfg, kern, ma, ma2, mb, g);
 }
 
 inline cudaError_t launch_ozaki_gemm(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
@@ -656,7 +677,7 @@ inline cudaError_t launch_slice_cols(const double* X, long long ld, int n, int m
     cudaError_t e = cudaMemsetAsync(colmax, 0, (size_t)m * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     colmax_kernel<<<dim3((m + 63) / 64, (n + 1023) / 1024), 256, 0, st>>>(X, ld, n, m, colmax);
-    slice_cols_kernel<<<dim3(m / 32, n / 128), 256, 0, st>>>(X, ld, n, m, colmax, planes, plane_stride, scale, nullptr, nullptr, nullptr, nullptr);
+    slice_cols_kernel<<<dim3(m / 32, n / 64), 128, 0, st>>>(X, ld, n, m, colmax, planes, plane_stride, scale, nullptr, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 
@@ -664,7 +685,7 @@ inline cudaError_t launch_slice_cols(const double* X, long long ld, int n, int m
 inline cudaError_t launch_slice_cols_pair(const double* X, long long ld, int n, int m, const double* w, const unsigned long long* colmaxX,
                                           const unsigned long long* colmaxWX, int8_t* planesX, int8_t* planesWX, long long plane_stride,
                                           double* scaleX, double* scaleWX, cudaStream_t st) {
-    slice_cols_kernel<<<dim3(m / 32, n / 128), 256, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
+    slice_cols_kernel<<<dim3(m / 32, n / 64), 128, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
     return cudaGetLastError();
 }
 

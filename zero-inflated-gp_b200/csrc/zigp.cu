@@ -41,6 +41,10 @@ struct Latent {
     int8_t* ozW[3] = {nullptr, nullptr, nullptr};
     double* ozWs[3] = {nullptr, nullptr, nullptr};
     double* Gf = nullptr;
+    // per-latent slice workspaces (the two latents run on two streams): row operand of the products, A / gv*A transposed
+    int8_t *oz_in = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;
+    double *oz_rs = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
+    unsigned long long* oz_colmax = nullptr;
     int nsplit_oz = 4;
 };
 
@@ -97,9 +101,9 @@ struct zigp_ctx {
     std::vector<ProfRec> prof;
     // contraction engine: 0 = DMMA (gemm_f64.cuh), 1 = fp64 on the int8 tensor cores (ozaki.cuh); dense path only
     int engine = 0;
-    int8_t *oz_in = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;     // slice planes: GEMM input (row-major), A / Aw transposed
-    double *oz_rs = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
-    unsigned long long* oz_colmax = nullptr;
+    bool oz_ready = false;
+    // second stream for latent g (the int8 contractions of one latent overlap the fp64 / memory-bound kernels of the other)
+    cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch of zigp_debug_gemm (int8 engine)
     int8_t *dbg_pa = nullptr, *dbg_pb = nullptr; double *dbg_sa = nullptr, *dbg_sb = nullptr;
     size_t dbg_cap_a = 0, dbg_cap_b = 0, dbg_cap_r = 0, dbg_cap_c = 0;
@@ -307,7 +311,7 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
 // int8 engine: one contraction of the chunk's sliced row operand (c->oz_in / c->oz_rs) with pre-sliced factor `wi` of the latent
 int oz_product(zigp_ctx* c, Latent& L, int wi, int rows, int tri, double* Out, double* stat_sq, double* stat_dot, const double* dotvec, cudaStream_t st) {
     const int Mp = L.Mp;
-    oz::OzOperand A{c->oz_in, Mp, rows, (long long)rows * Mp, c->oz_rs};
+    oz::OzOperand A{L.oz_in, Mp, rows, (long long)rows * Mp, L.oz_rs};
     oz::OzOperand B{L.ozW[wi], Mp, Mp, (long long)Mp * Mp, L.ozWs[wi]};
     oz::OzArgs a{};
     a.Out = Out; a.ldo = Mp; a.alpha = 1.0; a.beta = 0.0; a.rows = rows; a.cols = Mp; a.kdim = Mp; a.tri = tri;
@@ -317,9 +321,9 @@ int oz_product(zigp_ctx* c, Latent& L, int wi, int rows, int tri, double* Out, d
     c->launches++;
     return 0;
 }
-int oz_slice_in(zigp_ctx* c, const double* X, int rows, int Mp, cudaStream_t st) {
+int oz_slice_in(zigp_ctx* c, Latent& L, const double* X, int rows, int Mp, cudaStream_t st) {
     ProfScope ps(c, PC_SLICE, st);
-    CK(oz::launch_slice_rows(X, Mp, rows, Mp, nullptr, c->oz_in, (long long)rows * Mp, c->oz_rs, st));
+    CK(oz::launch_slice_rows(X, Mp, rows, Mp, nullptr, L.oz_in, (long long)rows * Mp, L.oz_rs, st));
     c->launches++;
     return 0;
 }
@@ -331,13 +335,13 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
     dim3 gk(Mp / 32, rows / 64);
     {
         ProfScope ps(c, PC_KGEN, st);
-        kgen_kernel<<<gk, 256, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, c->D, 0);
+        kgen_kernel<<<gk, 128, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, c->D, 0);
         LAUNCHED();
     }
     if (c->engine == 1 && rows % oz::OBM == 0) {
-        RUN(oz_slice_in(c, L.Kb, rows, Mp, st));
+        RUN(oz_slice_in(c, L, L.Kb, rows, Mp, st));
         RUN(oz_product(c, L, 0, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, st));               // A = K T^T, |A|^2, A.alpha_w
-        RUN(oz_slice_in(c, L.Ab, rows, Mp, st));
+        RUN(oz_slice_in(c, L, L.Ab, rows, Mp, st));
         RUN(oz_product(c, L, 1, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, st));       // |R A|^2 only: RA is never stored
         if (need_bwd) RUN(oz_product(c, L, 2, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, st));   // Y = G A
         return 0;
@@ -379,6 +383,50 @@ int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long lon
     return 0;
 }
 
+// backward of one chunk for one latent: Kmn-side gradient sums and the whitened rank update E += A^T diag(gv) A
+int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nvalid, int rows, cudaStream_t st) {
+    const int D = c->D;
+    Latent& L = c->lat[l];
+    KgradArgs k{};
+    k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
+    k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows; k.Aw = L.Vb; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
+    if (c->engine == 1) {          // the rank update slices A and gv*A itself: no Aw copy, but the column maxima of both
+        k.Aw = nullptr; k.cmaxA = L.oz_colmax; k.cmaxAw = L.oz_colmax + L.Mp;
+        CK(cudaMemsetAsync(L.oz_colmax, 0, (size_t)2 * L.Mp * sizeof(unsigned long long), st));
+    }
+    dim3 gg(L.Mp / 128, (rows + KG_ROWS - 1) / KG_ROWS);
+    {
+        ProfScope ps(c, PC_KGRAD, st);
+        kgrad_kernel<<<gg, 128, 0, st>>>(k);
+        LAUNCHED();
+    }
+    if (c->engine == 1) {
+        // E += Aw^T A on the int8 engine: the operands are the columns of Aw and A (k index = point), sliced transposed
+        {
+            ProfScope ps(c, PC_SLICE, st);
+            CK(oz::launch_slice_cols_pair(L.Ab, L.Mp, rows, L.Mp, L.gv, L.oz_colmax, L.oz_colmax + L.Mp, L.oz_colA, L.oz_colAw,
+                                          (long long)L.Mp * rows, L.oz_csA, L.oz_csAw, st));
+            c->launches++;
+        }
+        oz::OzOperand A{L.oz_colAw, rows, L.Mp, (long long)L.Mp * rows, L.oz_csAw};
+        oz::OzOperand B{L.oz_colA, rows, L.Mp, (long long)L.Mp * rows, L.oz_csA};
+        oz::OzArgs a{};
+        a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
+        a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
+        ProfScope ps(c, PC_SYRK, st);
+        CK(oz::launch_ozaki_gemm(A, B, a, st));
+        c->launches++;
+        return 0;
+    }
+    SyrkArgs s{};
+    s.Aw = L.Vb; s.A = L.Ab; s.lda = L.Mp; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
+    s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
+    ProfScope ps(c, PC_SYRK, st);
+    CK((launch_syrk_nt<ZIGP_SBT, ZIGP_SWM, ZIGP_SWN, ZIGP_SSTAGES, ZIGP_SMINB>(s, st)));
+    c->launches++;
+    return 0;
+}
+
 int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     if (!c->has_data) { c->err = "zigp: no data set (call zigp_set_data_* first)"; return ZIGP_ESTATE; }
     CK(cudaSetDevice(c->device));
@@ -391,53 +439,23 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
         CK(cudaMemsetAsync(L.kg_partial, 0, (size_t)c->kg_slots * (2 + 2 * D) * L.Mp * sizeof(double), st));
         RUN(mstage_forward(c, l, theta, st));
     }
+    // Latent f runs on the caller's stream, latent g on the context's auxiliary stream (fork / join with events around the
+    // likelihood kernel, which needs both): the tensor-core contractions of one latent overlap the fp64- and memory-bound
+    // kernels (kgen, slicing, kgrad) of the other.  Results do not depend on the interleaving (no floating-point atomics).
+    const bool two = c->engine == 1 && c->aux != nullptr;
+    cudaStream_t sl[2] = {st, two ? c->aux : st};
+    auto fork = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0)); } return 0; };
+    auto join = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_join, c->aux)); CK(cudaStreamWaitEvent(st, c->ev_join, 0)); } return 0; };
     for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
         const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
         const int rows = (int)rup(nvalid, 512);
-        for (int l = 0; l < 2; l++) RUN(chunk_forward(c, l, theta, c->X, n0, nvalid, rows, true, st));
+        RUN(fork());
+        for (int l = 0; l < 2; l++) RUN(chunk_forward(c, l, theta, c->X, n0, nvalid, rows, true, sl[l]));
+        RUN(join());
         RUN(run_point_kernel(c, theta, c->Y, n0, nvalid, rows, st));
-        for (int l = 0; l < 2; l++) {
-            Latent& L = c->lat[l];
-            KgradArgs k{};
-            k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
-            k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows; k.Aw = L.Vb; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
-            if (c->engine == 1) {          // the rank update slices A and gv*A itself: no Aw copy, but the column maxima of both
-                k.Aw = nullptr; k.cmaxA = c->oz_colmax; k.cmaxAw = c->oz_colmax + L.Mp;
-                CK(cudaMemsetAsync(c->oz_colmax, 0, (size_t)2 * L.Mp * sizeof(unsigned long long), st));
-            }
-            dim3 gg(L.Mp / 128, (rows + KG_ROWS - 1) / KG_ROWS);
-            {
-                ProfScope ps(c, PC_KGRAD, st);
-                kgrad_kernel<<<gg, 128, 0, st>>>(k);
-                LAUNCHED();
-            }
-            if (c->engine == 1) {
-                // E += Aw^T A on the int8 engine: the operands are the columns of Aw and A (k index = point), sliced transposed
-                {
-                    ProfScope ps(c, PC_SLICE, st);
-                    CK(oz::launch_slice_cols_pair(L.Ab, L.Mp, rows, L.Mp, L.gv, c->oz_colmax, c->oz_colmax + L.Mp, c->oz_colA, c->oz_colAw,
-                                                  (long long)L.Mp * rows, c->oz_csA, c->oz_csAw, st));
-                    c->launches++;
-                }
-                oz::OzOperand A{c->oz_colAw, rows, L.Mp, (long long)L.Mp * rows, c->oz_csAw};
-                oz::OzOperand B{c->oz_colA, rows, L.Mp, (long long)L.Mp * rows, c->oz_csA};
-                oz::OzArgs a{};
-                a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
-                a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
-                ProfScope ps(c, PC_SYRK, st);
-                CK(oz::launch_ozaki_gemm(A, B, a, st));
-                c->launches++;
-                continue;
-            }
-            SyrkArgs s{};
-            s.Aw = L.Vb; s.A = L.Ab; s.lda = L.Mp; s.E = L.E_splits; s.ldE = L.Mp; s.split_stride = (long long)L.Mp * L.Mp;
-            s.n = rows; s.m = L.Mp; s.nsplit = L.nsplit;
-            {
-                ProfScope ps(c, PC_SYRK, st);
-                CK((launch_syrk_nt<ZIGP_SBT, ZIGP_SWM, ZIGP_SWN, ZIGP_SSTAGES, ZIGP_SMINB>(s, st)));
-                c->launches++;
-            }
-        }
+        RUN(fork());
+        for (int l = 0; l < 2; l++) RUN(chunk_backward(c, l, theta, n0, nvalid, rows, sl[l]));
+        RUN(join());
     }
     // fold the per-CTA slots into the packed accumulator (fixed order -> deterministic)
     ProfScope psr(c, PC_REDUCE, st);
@@ -648,6 +666,7 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
                 if (fill > best + 0.02) { best = fill; ns = cand; }
             }
             L.nsplit = ns;
+            L.nsplit_oz = (int)std::max<long long>(4, (chunk + oz::MAX_ACC_K - 1) / oz::MAX_ACC_K);   // int32 accumulation stays exact per split
             DA(L.E_splits, (long long)std::max(ns, L.nsplit_oz) * MM);
         }
         return 0;
@@ -703,6 +722,9 @@ int zigp_destroy(zigp_ctx* c) {
     if (c->Xown) cudaFree(c->Xown);
     if (c->Yown) cudaFree(c->Yown);
     cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
+    if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->theta_pin) cudaFreeHost(c->theta_pin);
     if (c->out_pin) cudaFreeHost(c->out_pin);
     delete c;
@@ -894,24 +916,30 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
     if (!c || engine < 0 || engine > 1) return ZIGP_EINVAL;
     if (c->kron && engine == 1) { c->err = "zigp_set_engine: the int8 engine serves the dense path only"; return ZIGP_EINVAL; }
     CK(cudaSetDevice(c->device));
-    if (engine == 1 && !c->oz_in) {
+    if (engine == 1 && !c->oz_ready) {
         if (!oz::encode_fn()) { c->err = "zigp_set_engine: cuTensorMapEncodeTiled not available from this driver"; return ZIGP_ECUDA; }
+        if (std::max(c->lat[0].Mp, c->lat[1].Mp) > oz::MAX_ACC_K) { c->err = "zigp_set_engine: int8 engine supports up to 16384 inducing points per latent"; return ZIGP_EINVAL; }
         const long long chunk = c->chunk;
-        long long Mpmax = std::max(c->lat[0].Mp, c->lat[1].Mp);
         auto balloc = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, bytes)); c->allocs.push_back(*p); return 0; };
-        RUN(balloc((void**)&c->oz_in, (size_t)oz::NSL * chunk * Mpmax));
-        RUN(balloc((void**)&c->oz_colA, (size_t)oz::NSL * chunk * Mpmax));
-        RUN(balloc((void**)&c->oz_colAw, (size_t)oz::NSL * chunk * Mpmax));
-        RUN(balloc((void**)&c->oz_colmax, (size_t)2 * Mpmax * sizeof(unsigned long long)));
-        DA(c->oz_rs, chunk); DA(c->oz_csA, Mpmax); DA(c->oz_csAw, Mpmax);
         for (int l = 0; l < 2; l++) {
             Latent& L = c->lat[l];
+            RUN(balloc((void**)&L.oz_in, (size_t)oz::NSL * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_colA, (size_t)oz::NSL * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_colAw, (size_t)oz::NSL * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_colmax, (size_t)2 * L.Mp * sizeof(unsigned long long)));
+            DA(L.oz_rs, chunk); DA(L.oz_csA, L.Mp); DA(L.oz_csAw, L.Mp);
             for (int i = 0; i < 3; i++) {
                 RUN(balloc((void**)&L.ozW[i], (size_t)oz::NSL * L.Mp * L.Mp));
                 DA(L.ozWs[i], L.Mp);
             }
             DA(L.Gf, (long long)L.Mp * L.Mp);
         }
+        if (!getenv("ZIGP_ONE_STREAM")) {
+            CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        c->oz_ready = true;
     }
     c->engine = engine;
     return ZIGP_OK;
