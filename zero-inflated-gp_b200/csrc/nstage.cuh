@@ -169,7 +169,8 @@ struct KgradArgs {
     unsigned long long* cmaxA; unsigned long long* cmaxAw;   // int8 engine: per-column max |A|, max |gv A| over the chunk (bit patterns)
 };
 
-__global__ void __launch_bounds__(128, 6) kgrad_kernel(const KgradArgs p) {
+template <int DT>
+__global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
     __shared__ double sx[KG_ROWS][ZIGP_MAX_D];
     __shared__ double sgm[KG_ROWS], sgv[KG_ROWS];
     const int m = blockIdx.x * 128 + threadIdx.x;
@@ -183,9 +184,10 @@ __global__ void __launch_bounds__(128, 6) kgrad_kernel(const KgradArgs p) {
     for (int e = threadIdx.x; e < nr * p.D; e += 128) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
     for (int e = threadIdx.x; e < nr; e += 128) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
     __syncthreads();
-    double z[ZIGP_MAX_D], s1[ZIGP_MAX_D], q[ZIGP_MAX_D];
+    // DT = compile-time input dimension (1, 2, 3, 4 or ZIGP_MAX_D): keeps the per-dimension accumulators in as many registers as needed
+    double z[DT], s1[DT], q[DT];
 #pragma unroll
-    for (int d = 0; d < ZIGP_MAX_D; d++) { z[d] = (d < p.D && m < p.M) ? p.Z[m * p.D + d] : 0.0; s1[d] = 0.0; q[d] = 0.0; }
+    for (int d = 0; d < DT; d++) { z[d] = (d < p.D && m < p.M) ? p.Z[m * p.D + d] : 0.0; s1[d] = 0.0; q[d] = 0.0; }
     const double bm = p.beta[m];
     double s0 = 0.0, am = 0.0, mxa = 0.0, mxw = 0.0;
     const double* Kp = p.K + (long long)r0 * p.ld + m;
@@ -195,13 +197,14 @@ __global__ void __launch_bounds__(128, 6) kgrad_kernel(const KgradArgs p) {
 #pragma unroll 8
     for (int r = 0; r < nr; r++) {
         const double k = Kp[(long long)r * p.ld], yy = Yp[(long long)r * p.ld], aa = Ap[(long long)r * p.ld];
-        if (p.Aw) Awp[(long long)r * p.ld] = sgv[r] * aa;
-        mxa = fmax(mxa, fabs(aa)); mxw = fmax(mxw, fabs(sgv[r] * aa));
+        const double wa = sgv[r] * aa;
+        if (p.Aw) Awp[(long long)r * p.ld] = wa;
+        mxa = fmax(mxa, fabs(aa)); mxw = fmax(mxw, fabs(wa));
         const double G = (sgm[r] * bm - 2.0 * sgv[r] * yy) * k;
         s0 += G;
         am = fma(sgm[r], aa, am);
 #pragma unroll
-        for (int d = 0; d < ZIGP_MAX_D; d++) {
+        for (int d = 0; d < DT; d++) {
             if (d < p.D) { double df = sx[r][d] - z[d]; s1[d] = fma(G, df, s1[d]); q[d] = fma(G * df, df, q[d]); }
         }
     }
@@ -214,8 +217,18 @@ __global__ void __launch_bounds__(128, 6) kgrad_kernel(const KgradArgs p) {
     out[0] += s0;
     out[(long long)p.Mp] += am;
 #pragma unroll
-    for (int d = 0; d < ZIGP_MAX_D; d++) {
+    for (int d = 0; d < DT; d++) {
         if (d < p.D) { out[(long long)(2 + d) * p.Mp] += s1[d]; out[(long long)(2 + p.D + d) * p.Mp] += q[d]; }
+    }
+}
+
+inline void launch_kgrad(const KgradArgs& k, dim3 grid, cudaStream_t st) {
+    switch (k.D) {
+        case 1: kgrad_kernel<1><<<grid, 128, 0, st>>>(k); break;
+        case 2: kgrad_kernel<2><<<grid, 128, 0, st>>>(k); break;
+        case 3: kgrad_kernel<3><<<grid, 128, 0, st>>>(k); break;
+        case 4: kgrad_kernel<4><<<grid, 128, 0, st>>>(k); break;
+        default: kgrad_kernel<ZIGP_MAX_D><<<grid, 128, 0, st>>>(k); break;
     }
 }
 

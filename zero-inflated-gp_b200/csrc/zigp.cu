@@ -397,7 +397,7 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
     dim3 gg(L.Mp / 128, (rows + KG_ROWS - 1) / KG_ROWS);
     {
         ProfScope ps(c, PC_KGRAD, st);
-        kgrad_kernel<<<gg, 128, 0, st>>>(k);
+        launch_kgrad(k, gg, st);
         LAUNCHED();
     }
     if (c->engine == 1) {
@@ -442,7 +442,7 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     // Latent f runs on the caller's stream, latent g on the context's auxiliary stream (fork / join with events around the
     // likelihood kernel, which needs both): the tensor-core contractions of one latent overlap the fp64- and memory-bound
     // kernels (kgen, slicing, kgrad) of the other.  Results do not depend on the interleaving (no floating-point atomics).
-    const bool two = c->engine == 1 && c->aux != nullptr;
+    const bool two = c->engine == 1 && c->aux != nullptr && !c->profiling;     // per-kernel event timing wants the kernels alone on the GPU
     cudaStream_t sl[2] = {st, two ? c->aux : st};
     auto fork = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0)); } return 0; };
     auto join = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_join, c->aux)); CK(cudaStreamWaitEvent(st, c->ev_join, 0)); } return 0; };
