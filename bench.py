@@ -297,7 +297,7 @@ def run_ours(a):
     int8 = (not kron) and getattr(m, "engine", "dmma") == "int8"
     if int8:
         # int8 engine: per chunk and latent three launches of ozaki_gemm_kernel_v2 (A = K T^T lower, |R A|^2 upper, Y = G A full) =
-        # 4 M^2 fp64-equivalent flop per point per latent; each is 36 int8 slice products (8 x 7-bit slices, weights <= 7)
+        # 4 M^2 fp64-equivalent flop per point per latent; each fp64 product is NSL (NSL + 1) / 2 int8 slice products
         gflop = 2.0 * 4.0 * float(M) * M * n_loc
         achieved = gflop / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else 0.0
     if kron:
@@ -363,8 +363,10 @@ def roofline_head(int8, kron, achieved, dgemm_tf, M, m):
         bf16 = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
         src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a long, power-capped step)" if mp else "2 x 1400 (fallback: no MEASURED_PEAKS.json)"
         peak = 2.0 * (bf16 if bf16 else 1400.0)
-        return {"bound": "tensor", "kernel": "ozaki_gemm_kernel_v2<2> (tcgen05.mma kind::i8, 128x64 tiles, 8x7-bit slices = 36 slice products, TMA multicast in 2-CTA clusters, persistent)",
-                "achieved": achieved * 36.0, "peak": peak, "unit": "TOP/s", "frac": achieved * 36.0 / peak, "traffic": None,
+        from onoffgpf import _cabi
+        nsl, sbits, prods = _cabi.int8_config()
+        return {"bound": "tensor", "kernel": "ozaki_gemm_kernel_v2<2> (tcgen05.mma kind::i8, 128x64 tiles, %d x %d-bit slices = %d int8 slice products per fp64 product, TMA multicast in 2-CTA clusters, persistent)" % (nsl, sbits, prods),
+                "achieved": achieved * prods, "peak": peak, "unit": "TOP/s", "frac": achieved * prods / peak, "traffic": None, "slice_products": prods,
                 "peak_source": src, "fp64_equivalent_tflops": achieved, "dgemm_tflops_measured": dgemm_tf,
                 "fp64_equivalent_over_dgemm": achieved / dgemm_tf if dgemm_tf else None}
     return {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": dgemm_tf,

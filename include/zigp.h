@@ -102,6 +102,8 @@ int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_
  * same worst-case error bound as an fp64 dot product, ~2x the DMMA rate).  Allocates the slice workspaces on first use. */
 int zigp_set_engine(zigp_ctx* ctx, int engine);
 int zigp_get_engine(const zigp_ctx* ctx);
+/* build configuration of the int8 engine: slices per operand, bits per slice, int8 slice products per fp64 product (NSL (NSL+1) / 2) */
+int zigp_int8_config(int* slices, int* slice_bits, int* slice_products);
 /* Test hook: one contraction Out[r,c] = sum_k In[r,k] W[c,k] (tri: 0 full, 1 lower k <= c, 2 upper k >= c; optional per-row,
  * per-64-column-tile sums of squares) through engine 0 (DMMA, csrc/gemm_f64.cuh) or engine 1 (fp64 emulated on the int8 tensor
  * cores, csrc/ozaki.cuh), so that the two engines can be compared on the same operands. */

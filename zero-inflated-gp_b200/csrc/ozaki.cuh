@@ -22,7 +22,7 @@ namespace zigp {
 namespace oz {
 
 #ifndef ZIGP_OZ_SBITS
-#define ZIGP_OZ_SBITS 7
+#define ZIGP_OZ_SBITS 8
 #endif
 // Slice width.  8: seven signed 8-bit slices (digits in [-128, 127], |t| < 1/4 so that the leading digit fits), 28 slice products;
 // 7: eight 7-bit slices (digits in [-64, 64], |t| < 1/2), 36 slice products.  Both carry 55-56 bits below the row scale; int32
@@ -35,7 +35,7 @@ constexpr double INVB = (SBITS == 8) ? 1.0 / 256.0 : 1.0 / 128.0;
 constexpr double INVB2 = INVB * INVB;         // product scale 2^(-2 SBITS)
 constexpr int MAX_ACC_K = (SBITS == 8) ? 16384 : 32768;   // longest contraction accumulated in one int32 pass
 #ifndef ZIGP_OZ_SW
-#define ZIGP_OZ_SW 32
+#define ZIGP_OZ_SW 64
 #endif
 constexpr int OBM = 128, OBN = 64;            // tile rows, tile columns
 constexpr int UK = 32;                        // k depth of one tcgen05.mma kind::i8 (bytes == int8 elements)
@@ -329,6 +329,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
 #ifndef ZIGP_OZ_CL
 #define ZIGP_OZ_CL 2
 #endif
+#ifndef ZIGP_OZ_EXP
+#define ZIGP_OZ_EXP 0          // 1 / 2: bottleneck experiments (wrong results), see profiles/int8_bottleneck_r01.txt
+#endif
 constexpr int OZ_THREADS2 = 320;              // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quarter)
 
 __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
@@ -423,6 +426,10 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
                     const uint32_t ph = (gi / OSTAGES) & 1u;
                     const bool active = compute && k0 >= kb && k0 < ke;
                     tc05::mbar_wait(&empty[s], ph ^ 1u);
+#if ZIGP_OZ_EXP == 2
+                    tc05::mbar_arrive(&full[s]);            // experiment: no operand traffic at all (MMAs run on stale shared memory)
+                    continue;
+#endif
                     tc05::mbar_arrive_expect_tx(&full[s], A_STAGE + (active ? B_STAGE : 0));
                     uint8_t* dstA = sA + (size_t)s * A_STAGE + (size_t)rank * PL * OBM * OBK;
                     const CUtensorMap* mA = (NSL % CL != 0 && rank == CL - 1) ? &mapA2 : &mapA;
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
                     const bool active = compute && k0 >= kb && k0 < ke;
                     tc05::mbar_wait(&full[s], ph);
                     tc05::fence_after_thread_sync();
-                    if (active) {
+                    if (active && ZIGP_OZ_EXP != 1) {       // experiment 1: operand traffic and barriers only, no MMAs
                         const uint32_t a_base = tc05::smem_u32(sA + (size_t)s * A_STAGE);
                         const uint32_t b_base = tc05::smem_u32(sB + (size_t)s * B_STAGE);
 #pragma unroll

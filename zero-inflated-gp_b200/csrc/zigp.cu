@@ -947,6 +947,13 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
 
 int zigp_get_engine(const zigp_ctx* c) { return c ? c->engine : -1; }
 
+int zigp_int8_config(int* slices, int* slice_bits, int* slice_products) {
+    if (slices) *slices = oz::NSL;
+    if (slice_bits) *slice_bits = oz::SBITS;
+    if (slice_products) *slice_products = oz::NSL * (oz::NSL + 1) / 2;
+    return ZIGP_OK;
+}
+
 int zigp_set_profiling(zigp_ctx* c, int on) {
     if (!c) return ZIGP_EINVAL;
     cudaSetDevice(c->device);

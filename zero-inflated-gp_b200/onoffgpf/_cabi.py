@@ -33,6 +33,7 @@ SYMBOLS = {
     "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "zigp_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "zigp_get_engine": (C.c_int, [C.c_void_p]),
+    "zigp_int8_config": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "zigp_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "zigp_launch_count": (C.c_int64, [C.c_void_p]),
@@ -40,6 +41,13 @@ SYMBOLS = {
     "zigp_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "zigp_flop_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
+
+
+def int8_config():
+    """(slices per operand, bits per slice, int8 slice products per fp64 product) of the int8 engine as built"""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    lib().zigp_int8_config(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
 
 
 class ZigpError(RuntimeError):
