@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="dense", choices=["dense", "kron"],
                     help="dense: BASELINE.json configs[3] (the headline); kron: configs[4], Kronecker inducing grid Ms x Mt = 64 x 64 (secondary line)")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp64: the headline (matches the reference's float64); fp32: reduced-precision contractions (4 x 8-bit slices), secondary line")
+    ap.add_argument("--engine", default=None, choices=["int8", "dmma"])
     ap.add_argument("--ms", type=int, default=64)
     ap.add_argument("--mt", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0)
@@ -207,7 +210,8 @@ def run_ours(a):
     else:
         p = synth.make_params(M, M, D, seed=0)
         theta_h = torch.as_tensor(synth.pack_theta(p)).pin_memory()
-        m = synth.build_model(Xh.numpy(), Yh.numpy().reshape(-1, 1), p, device=dev, distributed=(world > 1), chunk_rows=(a.chunk or None))
+        m = synth.build_model(Xh.numpy(), Yh.numpy().reshape(-1, 1), p, device=dev, distributed=(world > 1), chunk_rows=(a.chunk or None),
+                              engine=a.engine, precision=a.precision)
     ctx = m._ctx
     theta = theta_h.to(dev)
     out = torch.empty(ctx.out_len, dtype=torch.float64, device=dev)
@@ -321,7 +325,8 @@ def run_ours(a):
         named = (N, M, D) == (1 << 24, 1024, 3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if a.precision == "fp64" else "f64 storage / 32-bit sliced contractions (reduced-precision mode, not the headline)", "data": "synthetic",
             "config": {"workload": (("BASELINE.json configs[4] (secondary line, not the headline): Kronecker inducing grid %d x %d (space x time), synthetic 2+1-D zero-inflated, N=%d, fp64" % (a.ms, a.mt, N))
                                     if kron else "BASELINE.json configs[3]: synthetic 3-D spatio-temporal zero-inflated, N=2^24 total, M=1024 per latent, RBF-ARD, fp64"
                                     if named else "synthetic zero-inflated N=%d D=%d M=%d fp64 (dev override, not the named config)" % (N, D, M)),
@@ -363,8 +368,7 @@ def roofline_head(int8, kron, achieved, dgemm_tf, M, m):
         bf16 = mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops")
         src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a long, power-capped step)" if mp else "2 x 1400 (fallback: no MEASURED_PEAKS.json)"
         peak = 2.0 * (bf16 if bf16 else 1400.0)
-        from onoffgpf import _cabi
-        nsl, sbits, prods = _cabi.int8_config()
+        nsl, sbits, prods = m._ctx.int8_config()
         return {"bound": "tensor", "kernel": "ozaki_gemm_kernel_v2<2> (tcgen05.mma kind::i8, 128x64 tiles, %d x %d-bit slices = %d int8 slice products per fp64 product, TMA multicast in 2-CTA clusters, persistent)" % (nsl, sbits, prods),
                 "achieved": achieved * prods, "peak": peak, "unit": "TOP/s", "frac": achieved * prods / peak, "traffic": None, "slice_products": prods,
                 "peak_source": src, "fp64_equivalent_tflops": achieved, "dgemm_tflops_measured": dgemm_tf,

@@ -98,12 +98,17 @@ int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xne
  * name: "L","T","Kmm","alpha_w","beta","E","a","G","K","A","RA","V","Y","mean","var","gm","gv" ; latent 0 = f, 1 = g. */
 int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
 /* Contraction engine of the dense path: 0 = DMMA (fp64 mma.sync, the default), 1 = fp64 emulated exactly-sliced on the INT8 tensor
- * cores (tcgen05.mma kind::i8; csrc/ozaki.cuh: 8 x 7-bit slices per operand, int32 accumulation in TMEM, fp64 recombination --
- * same worst-case error bound as an fp64 dot product, ~2x the DMMA rate).  Allocates the slice workspaces on first use. */
+ * cores (tcgen05.mma kind::i8; csrc/ozaki.cuh: 7 x 8-bit slices per operand, int32 accumulation in TMEM, fp64 recombination --
+ * same worst-case error bound as an fp64 dot product, ~2-3x the DMMA rate).  Allocates the slice workspaces on first use.
+ * zigp_create selects engine 1 unless the environment says ZIGP_ENGINE=dmma. */
 int zigp_set_engine(zigp_ctx* ctx, int engine);
 int zigp_get_engine(const zigp_ctx* ctx);
-/* build configuration of the int8 engine: slices per operand, bits per slice, int8 slice products per fp64 product (NSL (NSL+1) / 2) */
-int zigp_int8_config(int* slices, int* slice_bits, int* slice_products);
+/* configuration of the int8 engine of this context: slices per operand, bits per slice, int8 slice products per product (NS (NS+1) / 2) */
+int zigp_int8_config(const zigp_ctx* ctx, int* slices, int* slice_bits, int* slice_products);
+/* Precision of the N-scale contractions on the int8 engine: 0 = fp64 (7 x 8-bit slices, 55 bits below each row's scale, the default;
+ * results within the fp64 tolerances of the reference), 1 = reduced, fp32-class (4 x 8-bit slices, 31 bits, 10 instead of 28 slice
+ * products; the M-scale stage, the likelihood and all accumulations stay fp64).  BASELINE.json's "fp32 mode", tolerance rel 1e-4. */
+int zigp_set_precision(zigp_ctx* ctx, int mode);
 /* Test hook: one contraction Out[r,c] = sum_k In[r,k] W[c,k] (tri: 0 full, 1 lower k <= c, 2 upper k >= c; optional per-row,
  * per-64-column-tile sums of squares) through engine 0 (DMMA, csrc/gemm_f64.cuh) or engine 1 (fp64 emulated on the int8 tensor
  * cores, csrc/ozaki.cuh), so that the two engines can be compared on the same operands. */

@@ -62,3 +62,30 @@ def test_engines_agree_at_scale():
     full = np.linalg.norm(b[4:])
     for k in gb:
         assert np.linalg.norm(ga[k] - gb[k]) <= 1e-10 * np.linalg.norm(gb[k]) + 1e-13 * full, k
+
+
+@pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small"])
+def test_reduced_precision_mode_within_1e_4(name):
+    """BASELINE.json's fp32 mode (configs[2]: "fp32 and fp64"): contractions with 4 x 8-bit slices (31 bits below each row's scale),
+    everything else fp64; tolerance rel 1e-4 on the ELBO and on every gradient block (norm-wise), against the float64 oracle goldens"""
+    import os
+    from oracle import onoff_oracle as orc
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_%s.npz" % name))
+    N, Mf, Mg, D, seed, nd = (int(z[k]) for k in ("N", "Mf", "Mg", "D", "seed", "num_data"))
+    X, Y = synth.make_data(N, D, seed)
+    p = {k: z["p_" + k] for k in orc.PARAM_NAMES}
+    m = synth.build_model(X, Y, p, engine="int8", precision="fp32")
+    m.num_data = nd
+    assert m._ctx.int8_config() == (4, 8, 10)
+    m.build_likelihood()
+    out = m._last_out.cpu().numpy()
+    assert abs(out[0] - float(z["elbo"])) <= 1e-4 * abs(float(z["elbo"]))
+    g = synth.unpack_grad(out[4:], Mf, Mg, D)
+    full = np.sqrt(sum(float(np.sum(np.square(z["g_" + k]))) for k in orc.PARAM_NAMES))
+    worst = 0.0
+    for k in orc.PARAM_NAMES:
+        a, b = np.asarray(g[k]).reshape(-1), z["g_" + k].reshape(-1)
+        err = np.linalg.norm(a - b)
+        assert err <= 1e-4 * np.linalg.norm(b) + 1e-7 * full, (k, err / np.linalg.norm(b))
+        worst = max(worst, err / (np.linalg.norm(b) + 1e-300))
+    print("fp32-class mode, %s: ELBO rel err %.2e, worst gradient block rel err %.2e" % (name, abs(out[0] - float(z["elbo"])) / abs(float(z["elbo"])), worst))

@@ -1,18 +1,27 @@
-// fp64 contractions on the INT8 tensor cores (tcgen05.mma kind::i8) -- an error-free-transformation ("Ozaki") engine.
+// fp64 contractions on the INT8 tensor cores (tcgen05.mma kind::i8) -- an error-free-transformation ("Ozaki"-type) engine.
 //
 // B200 has no fp64 tcgen05 kind; DMMA tops out at 37 TFLOP/s while the int8 pipe delivers 8192 MAC/clk/SM.  An fp64 operand
-// row x[0..K) is scaled by a power of two to |t| < 1/2 and split exactly into NSL signed 7-bit slices,
-//     x = 2^e * sum_{p<NSL} X_p 2^(-7(p+1)) + r,   X_p in [-64, 64],   |r| <= 2^(e - 7 NSL - 1),
-// so a product of two sliced operands is   2^(e+f-14) * sum_w 2^(-7w) D_w ,  D_w = sum_{p+q=w} X_p . Y_q   (exact int32).
-// Keeping w <= NSL-1 (NSL(NSL+1)/2 = 36 slice products) leaves a relative error of ~NSL * 2^(-7 NSL) = 1e-16 of
-// (row max) x (column max) x K -- the same worst case as a native fp64 dot product of that length.
+// row x[0..K) is scaled by a power of two, t = x 2^-e with |t| < 1/4, and split exactly into NS signed 8-bit digits,
+//     t = sum_{p<NS} d_p 2^(-8(p+1)) + r,   d_p in [-128, 127] (|d_0| <= 65),   |r| <= 2^(-8 NS - 1),
+// so a product of two sliced operands is   2^(e+f-16) * sum_w 2^(-8w) D_w ,  D_w = sum_{p+q=w} d_p . d'_q   (exact in int32 for
+// contraction lengths up to MAX_ACC_K).  Only the weights w <= NS-1 are kept: NS (NS+1) / 2 int8 slice products.
+//   NS = 7 ("fp64" precision):  55 bits below each row's scale, 28 products; what is dropped is <= NS 2^(-8 NS) ~ 1e-16 of
+//                               (row max) x (column max) x K -- the worst-case bound of a native fp64 dot product of that length.
+//   NS = 4 ("fp32" precision):  31 bits below the row scale (fp32 carries 24), 10 products -- the reduced-precision mode.
 //
-// Tile: 128 rows x 64 columns.  TMEM holds the NSL = 8 weight accumulators side by side (8 x 64 = 512 columns); slice plane
+// Tile: 128 rows x 64 columns.  TMEM holds the NS weight accumulators side by side (NS x 64 <= 448 of 512 columns); slice plane
 // q of the 64-column operand occupies shared-memory rows [64 q, 64 q + 64), so ONE instruction
-//     A_p (128 x 32)  x  [B_0; ...; B_(7-p)] ((8-p) 64 x 32)  ->  TMEM columns [64 p, 512)
-// adds slice p's contribution to every weight >= p: 12 instructions per 32-deep k-step instead of 36.
-// Operands arrive by TMA (3-D boxes k x rows x planes, 32-byte swizzle) through a 4-stage mbarrier ring; one warp issues TMA,
-// one thread issues the MMAs, four warps drain TMEM (int32 -> fp64 Horner in 2^-7, power-of-two scales, fused row statistics).
+//     A_p (128 x 32)  x  [B_0; ...; B_(NS-1-p)] ((NS-p) 64 x 32)  ->  TMEM columns [64 p, 64 NS)
+// adds slice p's contribution to every weight >= p: 10 instructions per 32-deep k-step instead of 28 (NS = 7).
+// Operands arrive by TMA (3-D boxes k x rows x planes, 64-byte swizzle) through an mbarrier ring; warp 0 issues TMA, one thread of
+// warp 1 issues the MMAs, warps 2-9 drain TMEM (int32 -> fp64 Horner in 2^-8, power-of-two scales, fused row statistics).
+// A cluster of CL CTAs works on the same 128 rows and CL adjacent column tiles: per k-step each CTA fetches NS/CL slice planes of
+// the row operand and multicasts them to the whole cluster, so the L2 -> SM traffic of the big operand drops CL-fold.  A stage may
+// only be refilled when EVERY CTA of the cluster has released it, so the MMA warps commit to the empty barriers of all CTAs
+// (count CL).  In the triangular modes the column tiles of a cluster have different k ranges; every CTA walks the union, loads
+// its column operand and issues MMAs only inside its own range.  CTAs are persistent (cluster c takes cluster-tiles c, c +
+// #clusters, ...): barrier set-up, TMEM allocation and the pipeline fill are paid once, and the producer runs ahead into the next
+// tile while the epilogue drains TMEM.  (evidence in profiles/int8_bottleneck_r01.txt.)
 #pragma once
 #include "tc05.cuh"
 #include "gemm_f64.cuh"
@@ -21,45 +30,52 @@
 namespace zigp {
 namespace oz {
 
-#ifndef ZIGP_OZ_SBITS
-#define ZIGP_OZ_SBITS 8
-#endif
-// Slice width.  8: seven signed 8-bit slices (digits in [-128, 127], |t| < 1/4 so that the leading digit fits), 28 slice products;
-// 7: eight 7-bit slices (digits in [-64, 64], |t| < 1/2), 36 slice products.  Both carry 55-56 bits below the row scale; int32
-// accumulation is exact for contraction lengths up to 2^31 / (2^(2 SBITS) NSL): 18724 (8-bit) / 65536 (7-bit) per accumulation.
-constexpr int SBITS = ZIGP_OZ_SBITS;
-constexpr int NSL = 56 / SBITS;               // slices per operand (7 or 8)
-constexpr int NPA = NSL;                      // slice planes per shared-memory stage of the row operand
-constexpr int EOFF = (SBITS == 8) ? 3 : 2;    // exponent offset: |x| 2^-e < 2^(1 - EOFF)
-constexpr double INVB = (SBITS == 8) ? 1.0 / 256.0 : 1.0 / 128.0;
+constexpr int NS64 = 7;                       // slices per operand, fp64 precision
+constexpr int NS32 = 4;                       // slices per operand, fp32-class precision
+constexpr int SBITS = 8;                      // bits per slice
+constexpr int EOFF = 3;                       // exponent offset: |x| 2^-e < 1/4, so the leading digit fits a signed byte
+constexpr double INVB = 1.0 / 256.0;
 constexpr double INVB2 = INVB * INVB;         // product scale 2^(-2 SBITS)
-constexpr int MAX_ACC_K = (SBITS == 8) ? 16384 : 32768;   // longest contraction accumulated in one int32 pass
-#ifndef ZIGP_OZ_SW
-#define ZIGP_OZ_SW 64
+constexpr int MAX_ACC_K = 16384;              // longest contraction accumulated in one int32 pass: 7 * 2^14 * K < 2^31
+#ifndef ZIGP_OZ_CL
+#define ZIGP_OZ_CL 2
+#endif
+#ifndef ZIGP_OZ_EXP
+#define ZIGP_OZ_EXP 0          // 1 / 2: bottleneck experiments (wrong results), see profiles/int8_bottleneck_r01.txt
 #endif
 constexpr int OBM = 128, OBN = 64;            // tile rows, tile columns
 constexpr int UK = 32;                        // k depth of one tcgen05.mma kind::i8 (bytes == int8 elements)
-constexpr int OBK = ZIGP_OZ_SW;               // k bytes per pipeline stage == TMA swizzle span (32 / 64 / 128)
-constexpr int OSTAGES = (SBITS == 8 ? 5 : 4) * 32 / OBK;   // 5 x 42 KB (seven slices) or 4 x 48 KB (eight slices) at the 32-byte span
-constexpr int A_STAGE = NPA * OBM * OBK;
-constexpr int B_STAGE = NSL * OBN * OBK;
-constexpr int OZ_THREADS = 192;               // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
-constexpr size_t OZ_SMEM = (size_t)OSTAGES * (A_STAGE + B_STAGE) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int OBK = 64;                       // k bytes per pipeline stage == TMA swizzle span (32-byte rows are delivery-bound)
+constexpr int OZ_THREADS = 320;               // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quarter)
+
+template <int NS>
+struct Cfg {
+    static constexpr int A_STAGE = NS * OBM * OBK;
+    static constexpr int B_STAGE = NS * OBN * OBK;
+    static constexpr int STAGES = (NS > 4) ? 2 : 4;     // 2 x 84 KB (NS = 7) or 4 x 48 KB (NS = 4)
+    static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int PRODUCTS = NS * (NS + 1) / 2;
+};
 
 // ---- slicing ------------------------------------------------------------------------------------------------------------
-// 56 fractional bits of t (|t| < 2^(1-EOFF)) as NSL balanced base-2^SBITS digits, most significant first:
-//     t ~= sum_p d[p] 2^(-SBITS (p+1)),   d[p>0] in [-2^(SBITS-1), 2^(SBITS-1) - 1],  |d[0]| <= 2^(SBITS-2) + 1.
-// Two double -> int32 roundings (28 bits each) and integer digit extraction: the per-slice F2I / I2F chain of the obvious loop
-// is fp64-conversion bound.
-__device__ __forceinline__ void slice8(double t, int (&d)[NSL]) {
-    const double v1 = t * 268435456.0;                 // 2^28, exact
-    const int h1 = __double2int_rn(v1);
-    const double v2 = (v1 - (double)h1) * 268435456.0; // exact remainder, |.| <= 2^27
-    const int h2 = __double2int_rn(v2);
-    long long V = ((long long)h1 << 28) + (long long)h2;    // round(t 2^56)
+// 8 NS fractional bits of t (|t| < 1/4) as NS balanced base-256 digits, most significant first.  NS = 7: two double -> int32
+// roundings (28 bits each) and integer digit extraction (the per-slice F2I / I2F chain of the obvious loop is fp64-conversion
+// bound); NS = 4: one rounding to 32 bits.
+template <int NS>
+__device__ __forceinline__ void slice_digits(double t, int (&d)[NS]) {
+    long long V;
+    if (NS * SBITS > 52) {
+        const double v1 = t * 268435456.0;                 // 2^28, exact
+        const int h1 = __double2int_rn(v1);
+        const double v2 = (v1 - (double)h1) * 268435456.0; // exact remainder, |.| <= 2^27
+        const int h2 = __double2int_rn(v2);
+        V = ((long long)h1 << 28) + (long long)h2;         // round(t 2^56)
+    } else {
+        V = __double2ll_rn(t * (double)(1LL << (NS * SBITS)));
+    }
     constexpr long long HALF = 1LL << (SBITS - 1), MASK = (1LL << SBITS) - 1;
 #pragma unroll
-    for (int i = NSL - 1; i >= 1; i--) {
+    for (int i = NS - 1; i >= 1; i--) {
         const long long lo = ((V + HALF) & MASK) - HALF;
         d[i] = (int)lo; V = (V - lo) >> SBITS;
     }
@@ -67,6 +83,7 @@ __device__ __forceinline__ void slice8(double t, int (&d)[NSL]) {
 }
 
 // planes[p][r][k] = X_p of row r (k contiguous, plane stride in bytes), scale[r] = 2^e.  One warp per row; K % 128 == 0.
+template <int NS>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ X, long long ld, int rows, int K,
                                                           const double* __restrict__ rowweight, int8_t* __restrict__ planes,
                                                           long long plane_stride, double* __restrict__ scale) {
@@ -89,11 +106,11 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     for (int k = lane * 4; k < K; k += 128) {
         const double4 v = *reinterpret_cast<const double4*>(x + k);
         const double t[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
-        int d[4][NSL];
+        int d[4][NS];
 #pragma unroll
-        for (int j = 0; j < 4; j++) slice8(t[j], d[j]);
+        for (int j = 0; j < 4; j++) slice_digits<NS>(t[j], d[j]);
 #pragma unroll
-        for (int p = 0; p < NSL; p++) {
+        for (int p = 0; p < NS; p++) {
             const uint32_t pk = (uint32_t)(d[0][p] & 0xff) | ((uint32_t)(d[1][p] & 0xff) << 8) | ((uint32_t)(d[2][p] & 0xff) << 16) | ((uint32_t)(d[3][p] & 0xff) << 24);
             *reinterpret_cast<uint32_t*>(out + (long long)p * plane_stride + k) = pk;
         }
@@ -120,6 +137,7 @@ __global__ void __launch_bounds__(256) colmax_kernel(const double* __restrict__ 
 
 // Pass 2: slice a 64 (n) x 32 (columns) tile per block and write it transposed.  n % 64 == 0, m % 32 == 0.
 // With rowweight the kernel also emits the slices of diag(rowweight) X (planes2 / scale2, maxima colmax2) from the same read.
+template <int NS>
 __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restrict__ X, long long ld, int n, int m,
                                                           const unsigned long long* __restrict__ colmax, int8_t* __restrict__ planes,
                                                           long long plane_stride, double* __restrict__ scale,
@@ -144,20 +162,20 @@ __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restric
         const double inv = scalbn(1.0, -e);
         if (blockIdx.y == 0 && grp == 0) (pass ? scale2 : scale)[c0 + cc] = scalbn(1.0, e);
         int8_t* out = (pass ? planes2 : planes) + (long long)(c0 + cc) * n + n0 + grp * 16;
-        uint32_t w[NSL][4];
+        uint32_t w[NS][4];
 #pragma unroll
-        for (int p = 0; p < NSL; p++) { w[p][0] = 0; w[p][1] = 0; w[p][2] = 0; w[p][3] = 0; }
+        for (int p = 0; p < NS; p++) { w[p][0] = 0; w[p][1] = 0; w[p][2] = 0; w[p][3] = 0; }
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             double x = tile[grp * 16 + j][cc];
             if (pass) x *= sw[grp * 16 + j];
-            int d[NSL];
-            slice8(x * inv, d);
+            int d[NS];
+            slice_digits<NS>(x * inv, d);
 #pragma unroll
-            for (int p = 0; p < NSL; p++) w[p][j >> 2] |= (uint32_t)(d[p] & 0xff) << (8 * (j & 3));
+            for (int p = 0; p < NS; p++) w[p][j >> 2] |= (uint32_t)(d[p] & 0xff) << (8 * (j & 3));
         }
 #pragma unroll
-        for (int p = 0; p < NSL; p++) *reinterpret_cast<uint4*>(out + (long long)p * plane_stride) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+        for (int p = 0; p < NS; p++) *reinterpret_cast<uint4*>(out + (long long)p * plane_stride) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
     }
 }
 
@@ -174,175 +192,16 @@ struct OzArgs {
     int nsplit; long long split_stride;         // TRI_FULL only: the k range is dealt to gridDim.y splits, split s writes Out + s * split_stride
 };
 
-__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                  const __grid_constant__ CUtensorMap mapB, const OzArgs g) {
-    extern __shared__ uint8_t oz_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)OSTAGES * A_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)OSTAGES * (A_STAGE + B_STAGE));
-    uint64_t* full = bars;                  // [OSTAGES]
-    uint64_t* empty = bars + OSTAGES;       // [OSTAGES]
-    uint64_t* tmem_full = bars + 2 * OSTAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OSTAGES + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates (row tiles fastest, column tiles heaviest-first for the triangular modes)
-    const int ntr = g.rows / OBM, ntc = g.cols / OBN;
-    const int tr = blockIdx.x % ntr;
-    const int tcx = blockIdx.x / ntr;
-    const int tc = (g.tri == TRI_LOWER) ? (ntc - 1 - tcx) : tcx;
-    const int row0 = tr * OBM, col0 = tc * OBN;
-    if (g.lower_only && col0 > row0 + OBM - 1) return;       // whole CTA leaves before any barrier / allocation
-
-    int kbeg = 0, kend = g.kdim;
-    if (g.tri == TRI_LOWER) kend = min(g.kdim, (col0 + OBN + OBK - 1) / OBK * OBK);     // the factor is zero beyond its triangle
-    if (g.tri == TRI_UPPER) kbeg = col0 / OBK * OBK;
-    if (g.nsplit > 1) {
-        const long long S = g.kdim / OBK;
-        kbeg = (int)(S * blockIdx.y / g.nsplit) * OBK;
-        kend = (int)(S * (blockIdx.y + 1) / g.nsplit) * OBK;
-    }
-    const int nk = (kend - kbeg) / OBK;
-
-    if (warp == 0 && lane == 0) {
-        tc05::prefetch_tensormap(&mapA);
-        tc05::prefetch_tensormap(&mapB);
-    }
-    if (warp == 1) {
-        if (lane == 0) {
-            for (int s = 0; s < OSTAGES; s++) { tc05::mbar_init(&full[s], 1); tc05::mbar_init(&empty[s], 1); }
-            tc05::mbar_init(tmem_full, 1);
-            tc05::fence_barrier_init();
-        }
-        __syncwarp();
-        tc05::tmem_alloc<512>(tmem_slot);
-    }
-    tc05::fence_before_thread_sync();
-    __syncthreads();
-    tc05::fence_after_thread_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int it = 0; it < nk; it++) {
-                const int s = it % OSTAGES;
-                const uint32_t ph = (uint32_t)(it / OSTAGES) & 1u;
-                tc05::mbar_wait(&empty[s], ph ^ 1u);
-                tc05::mbar_arrive_expect_tx(&full[s], A_STAGE + B_STAGE);
-                const int k0 = kbeg + it * OBK;
-                tc05::tma_load_3d(sA + (size_t)s * A_STAGE, &mapA, &full[s], k0, row0, 0);
-                tc05::tma_load_3d(sB + (size_t)s * B_STAGE, &mapB, &full[s], k0, col0, 0);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            for (int it = 0; it < nk; it++) {
-                const int s = it % OSTAGES;
-                const uint32_t ph = (uint32_t)(it / OSTAGES) & 1u;
-                tc05::mbar_wait(&full[s], ph);
-                tc05::fence_after_thread_sync();
-                const uint32_t a_base = tc05::smem_u32(sA + (size_t)s * A_STAGE);
-                const uint32_t b_base = tc05::smem_u32(sB + (size_t)s * B_STAGE);
-#pragma unroll
-                for (int ks = 0; ks < OBK / UK; ks++) {               // 32-byte sub-steps inside the swizzle span
-#pragma unroll
-                    for (int p = 0; p < NSL; p++) {
-                        const uint64_t da = tc05::smem_desc_kmajor<OBK>(a_base + p * (OBM * OBK) + ks * UK);
-                        int nrem = (NSL - p) * OBN, off = 0;
-                        while (nrem > 0) {
-                            const int n = nrem > 256 ? 256 : nrem;
-                            const uint64_t db = tc05::smem_desc_kmajor<OBK>(b_base + off * OBK + ks * UK);
-                            tc05::mma_i8(tmem_base + (uint32_t)(p * OBN + off), da, db, tc05::idesc_i8(OBM, n), (it > 0 || ks > 0 || p > 0) ? 1u : 0u);
-                            off += n; nrem -= n;
-                        }
-                    }
-                }
-                tc05::mma_commit(&empty[s]);            // frees the stage when these MMAs have read it
-            }
-            tc05::mma_commit(tmem_full);                // accumulators complete
-        }
-    } else {
-        // ===== epilogue: TMEM -> fp64 =====
-        const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int rl = q * 32 + lane;
-        const int r = row0 + rl;
-        tc05::mbar_wait(tmem_full, 0);
-        tc05::fence_after_thread_sync();
-        const double rs = g.rscale[r] * INVB2;
-        double* Out = g.Out + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0);
-        const double* Zin = g.Zin ? g.Zin + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0) : nullptr;
-        double ssq = 0.0, sdt = 0.0;
-        for (int c0 = 0; c0 < OBN; c0 += 16) {
-            double acc[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] = 0.0;
-#pragma unroll
-            for (int w = NSL - 1; w >= 0; w--) {
-                uint32_t v[16];
-                tc05::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(w * OBN + c0), v);
-                tc05::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], INVB, (double)(int)v[j]);
-            }
-            const int c = col0 + c0;
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                double v0 = g.alpha * (acc[j] * rs * g.cscale[c + j]);
-                double v1 = g.alpha * (acc[j + 1] * rs * g.cscale[c + j + 1]);
-                if (g.beta != 0.0) {
-                    const double2 z = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j);
-                    v0 += g.beta * z.x; v1 += g.beta * z.y;
-                }
-                if (g.Out) *reinterpret_cast<double2*>(Out + (long long)r * g.ldo + c + j) = make_double2(v0, v1);
-                if (g.OutSq) *reinterpret_cast<double2*>(g.OutSq + (long long)r * g.ldo + c + j) = make_double2(v0 * v0, v1 * v1);
-                if (g.stat_sq) {
-                    ssq = fma(v0, v0, ssq); ssq = fma(v1, v1, ssq);
-                    if (g.dotvec) { sdt = fma(v0, g.dotvec[c + j], sdt); sdt = fma(v1, g.dotvec[c + j + 1], sdt); }
-                }
-            }
-        }
-        if (g.stat_sq) {
-            g.stat_sq[(long long)tc * g.rows + r] = ssq;
-            if (g.stat_dot) g.stat_dot[(long long)tc * g.rows + r] = sdt;
-        }
-    }
-    tc05::fence_before_thread_sync();
-    __syncthreads();
-    if (warp == 1) {
-        tc05::fence_after_thread_sync();
-        tc05::tmem_dealloc<512>(tmem_base);
-    }
-}
-
-// ---- v2: persistent CTAs, thread-block clusters with TMA multicast of the row operand, 8 epilogue warps ----------------------
-// A cluster of CL CTAs works on the same 128 rows and CL adjacent column tiles.  Per k-step each CTA fetches NSL/CL slice planes
-// of the row operand and multicasts them to the whole cluster, so the L2 -> SM traffic of the big operand drops CL-fold (v1 is
-// bound by it: 48 KB per k-step per SM is ~8 TB/s chip-wide).  A stage may only be refilled when EVERY CTA of the cluster has
-// released it, so the MMA warps commit to the empty barriers of all CTAs (count CL).  In the triangular modes the column tiles
-// of a cluster have different k ranges; every CTA walks the union, loads its column operand and issues MMAs only inside its
-// own range.  CTAs are persistent (cluster c takes cluster-tiles c, c + #clusters, ...): barrier set-up, TMEM allocation and the
-// pipeline fill are paid once, and the producer runs ahead into the next tile while the epilogue drains TMEM.
-#ifndef ZIGP_OZ_CL
-#define ZIGP_OZ_CL 2
-#endif
-#ifndef ZIGP_OZ_EXP
-#define ZIGP_OZ_EXP 0          // 1 / 2: bottleneck experiments (wrong results), see profiles/int8_bottleneck_r01.txt
-#endif
-constexpr int OZ_THREADS2 = 320;              // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quarter)
-
 __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
     int n = 0;
     for (int tr = 0; tr < ntr; tr++) { const int cnt = (tr * OBM + OBM - 1) / (CL * OBN) + 1; n += cnt < ntcg ? cnt : ntcg; }
     return n;
 }
 
-template <int CL>
-__global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+template <int NS, int CL>
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                                                                       const __grid_constant__ CUtensorMap mapB, const OzArgs g) {
+    constexpr int A_STAGE = Cfg<NS>::A_STAGE, B_STAGE = Cfg<NS>::B_STAGE, OSTAGES = Cfg<NS>::STAGES;
     extern __shared__ uint8_t oz_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -360,7 +219,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
     const uint32_t cid = (CL > 1) ? tc05::cluster_id_x() : blockIdx.x;
     const uint32_t ncl = (CL > 1) ? tc05::num_clusters_x() : gridDim.x;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
-    constexpr int PL = (NSL + CL - 1) / CL; // slice planes of the row operand fetched by each CTA (mapA: PL planes; the last rank takes the remainder through mapA2)
+    constexpr int PL = (NS + CL - 1) / CL; // slice planes of the row operand fetched by each CTA (mapA: PL planes; the last rank takes the remainder through mapA2)
 
     const int ntr = g.rows / OBM, ntc = g.cols / OBN, ntcg = ntc / CL;
     // rank-update mode enumerates only the cluster-tiles that touch the lower triangle (row tile tr owns tcg <= (128 tr + 127) / (CL 64))
@@ -432,7 +291,7 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
 #endif
                     tc05::mbar_arrive_expect_tx(&full[s], A_STAGE + (active ? B_STAGE : 0));
                     uint8_t* dstA = sA + (size_t)s * A_STAGE + (size_t)rank * PL * OBM * OBK;
-                    const CUtensorMap* mA = (NSL % CL != 0 && rank == CL - 1) ? &mapA2 : &mapA;
+                    const CUtensorMap* mA = (NS % CL != 0 && rank == CL - 1) ? &mapA2 : &mapA;
                     if (CL > 1) tc05::tma_load_3d_mcast(dstA, mA, &full[s], k0, row0, (int)rank * PL, CMASK);
                     else tc05::tma_load_3d(dstA, mA, &full[s], k0, row0, 0);
                     if (active) tc05::tma_load_3d(sB + (size_t)s * B_STAGE, &mapB, &full[s], k0, col0, 0);
@@ -464,9 +323,9 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
 #pragma unroll
                         for (int ks = 0; ks < OBK / UK; ks++) {
 #pragma unroll
-                            for (int p = 0; p < NSL; p++) {
+                            for (int p = 0; p < NS; p++) {
                                 const uint64_t da = tc05::smem_desc_kmajor<OBK>(a_base + p * (OBM * OBK) + ks * UK);
-                                int nrem = (NSL - p) * OBN, off = 0;
+                                int nrem = (NS - p) * OBN, off = 0;
                                 while (nrem > 0) {
                                     const int n = nrem > 256 ? 256 : nrem;
                                     const uint64_t db = tc05::smem_desc_kmajor<OBK>(b_base + off * OBK + ks * UK);
@@ -501,15 +360,15 @@ __global__ void __launch_bounds__(OZ_THREADS2, 1) ozaki_gemm_kernel_v2(const __g
 #pragma unroll
                 for (int j = 0; j < 16; j++) acc[ch][j] = 0.0;
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32 + ch * 16);
-                if (NSL & 1) {                              // odd slice count: the top weight alone
+                if (NS & 1) {                              // odd slice count: the top weight alone
                     uint32_t v0[16];
-                    tc05::tmem_ld16(ta + (uint32_t)((NSL - 1) * OBN), v0);
+                    tc05::tmem_ld16(ta + (uint32_t)((NS - 1) * OBN), v0);
                     tc05::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; j++) acc[ch][j] = __hiloint2double(0x43300000, (int)(v0[j] ^ 0x80000000u)) - 4503601774854144.0;
                 }
 #pragma unroll
-                for (int w = (NSL & ~1) - 1; w >= 0; w -= 2) {
+                for (int w = (NS & ~1) - 1; w >= 0; w -= 2) {
                     uint32_t v0[16], v1[16];
                     tc05::tmem_ld16(ta + (uint32_t)(w * OBN), v0);
                     tc05::tmem_ld16(ta + (uint32_t)((w - 1) * OBN), v1);
@@ -588,11 +447,11 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// tensor map over slice planes [NSL][nrows][K] (int8, K contiguous): box = OBK x box_rows x NSL, 32-byte swizzle
-inline bool make_plane_map(CUtensorMap* map, const int8_t* planes, long long K, long long nrows, long long plane_stride, int box_rows, int box_planes = NSL) {
+// tensor map over slice planes [ns][nrows][K] (int8, K contiguous): box = OBK x box_rows x box_planes, 64-byte swizzle
+inline bool make_plane_map(CUtensorMap* map, const int8_t* planes, long long K, long long nrows, long long plane_stride, int ns, int box_rows, int box_planes) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)nrows, (cuuint64_t)NSL};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)nrows, (cuuint64_t)ns};
     cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)plane_stride};
     cuuint32_t box[3] = {(cuuint32_t)OBK, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -601,38 +460,17 @@ inline bool make_plane_map(CUtensorMap* map, const int8_t* planes, long long K, 
               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct OzOperand {                   // a sliced matrix: NSL planes of nrows x K int8 + one power-of-two scale per row
+struct OzOperand {                   // a sliced matrix: ns planes of nrows x K int8 + one power-of-two scale per row
     const int8_t* planes; long long K; long long nrows; long long plane_stride; const double* scale;
 };
 
-#ifndef ZIGP_OZ_V
-#define ZIGP_OZ_V 2
-#endif
-
-inline cudaError_t launch_ozaki_gemm_v1(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    CUtensorMap ma, mb;
-    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, OBM, NPA)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, OBN)) return cudaErrorInvalidValue;
-    g.rscale = A.scale; g.cscale = B.scale;
-    if (g.nsplit < 1) g.nsplit = 1;
-    dim3 grid((g.rows / OBM) * (g.cols / OBN), g.nsplit);
-    ozaki_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(ma, mb, g);
-    return cudaGetLastError();
-}
-
-template <int CL>
-inline cudaError_t launch_ozaki_gemm_v2(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
-    auto kern = ozaki_gemm_kernel_v2<CL>;
+template <int NS, int CL>
+inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
+    auto kern = ozaki_gemm_kernel<NS, CL>;
     static bool attr_done = false;
     static int n_sms = 0;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NS>::SMEM);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -640,10 +478,10 @@ inline cudaError_t launch_ozaki_gemm_v2(const OzOperand& A, const OzOperand& B, 
         attr_done = true;
     }
     CUtensorMap ma, ma2, mb;
-    constexpr int PL = (NSL + CL - 1) / CL, PL2 = NSL - PL * (CL - 1);
-    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, OBM, PL)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&ma2, A.planes, A.K, A.nrows, A.plane_stride, OBM, PL2 > 0 ? PL2 : PL)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, OBN)) return cudaErrorInvalidValue;
+    constexpr int PL = (NS + CL - 1) / CL, PL2 = NS - PL * (CL - 1);
+    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, NS, OBM, PL)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&ma2, A.planes, A.K, A.nrows, A.plane_stride, NS, OBM, PL2 > 0 ? PL2 : PL)) return cudaErrorInvalidValue;
+    if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, NS, OBN, NS)) return cudaErrorInvalidValue;
     g.rscale = A.scale; g.cscale = B.scale;
     if (g.nsplit < 1) g.nsplit = 1;
     const int ntiles = g.lower_only ? lower_tile_count(g.rows / OBM, (g.cols / OBN) / CL, CL) : (g.rows / OBM) * ((g.cols / OBN) / CL);   // cluster-tiles
@@ -651,8 +489,8 @@ inline cudaError_t launch_ozaki_gemm_v2(const OzOperand& A, const OzOperand& B, 
     ncl = std::min(ncl, ntiles);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(ncl * CL), (unsigned)g.nsplit, 1);
-    cfg.blockDim = dim3(OZ_THREADS2, 1, 1);
-    cfg.dynamicSmemBytes = OZ_SMEM;
+    cfg.blockDim = dim3(OZ_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<NS>::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -661,38 +499,30 @@ inline cudaError_t launch_ozaki_gemm_v2(const OzOperand& A, const OzOperand& B, 
     return cudaLaunchKernelEx(&cfg, kern, ma, ma2, mb, g);
 }
 
-inline cudaError_t launch_ozaki_gemm(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
-#if ZIGP_OZ_V == 1
-    return launch_ozaki_gemm_v1(A, B, g, st);
-#else
-    const int ntc = g.cols / OBN;
-    if (ZIGP_OZ_CL >= 4 && ntc % 4 == 0) return launch_ozaki_gemm_v2<4>(A, B, g, st);
-    if (ZIGP_OZ_CL >= 2 && ntc % 2 == 0) return launch_ozaki_gemm_v2<2>(A, B, g, st);
-    return launch_ozaki_gemm_v2<1>(A, B, g, st);
-#endif
+// ns = 7 (fp64 precision) or 4 (fp32-class precision); operands must have been sliced with the same ns
+inline cudaError_t launch_ozaki_gemm(int ns, const OzOperand& A, const OzOperand& B, const OzArgs& g, cudaStream_t st) {
+    const bool pair = ZIGP_OZ_CL >= 2 && (g.cols / OBN) % 2 == 0;
+    if (ns == NS64) return pair ? launch_ozaki_gemm_t<NS64, 2>(A, B, g, st) : launch_ozaki_gemm_t<NS64, 1>(A, B, g, st);
+    if (ns == NS32) return pair ? launch_ozaki_gemm_t<NS32, 2>(A, B, g, st) : launch_ozaki_gemm_t<NS32, 1>(A, B, g, st);
+    return cudaErrorInvalidValue;
 }
 
-inline cudaError_t launch_slice_rows(const double* X, long long ld, int rows, int K, const double* rowweight, int8_t* planes, long long plane_stride,
-                                     double* scale, cudaStream_t st) {
-    slice_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(X, ld, rows, K, rowweight, planes, plane_stride, scale);
-    return cudaGetLastError();
-}
-
-// planes[p][c][n] <- columns of X (n x m), scale[c]; colmax is an m-long scratch
-inline cudaError_t launch_slice_cols(const double* X, long long ld, int n, int m, unsigned long long* colmax, int8_t* planes, long long plane_stride,
-                                     double* scale, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(colmax, 0, (size_t)m * sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
-    colmax_kernel<<<dim3((m + 63) / 64, (n + 1023) / 1024), 256, 0, st>>>(X, ld, n, m, colmax);
-    slice_cols_kernel<<<dim3(m / 32, n / 64), 128, 0, st>>>(X, ld, n, m, colmax, planes, plane_stride, scale, nullptr, nullptr, nullptr, nullptr);
+inline cudaError_t launch_slice_rows(int ns, const double* X, long long ld, int rows, int K, int8_t* planes, long long plane_stride, double* scale,
+                                     cudaStream_t st) {
+    if (ns == NS64) slice_rows_kernel<NS64><<<(rows + 7) / 8, 256, 0, st>>>(X, ld, rows, K, nullptr, planes, plane_stride, scale);
+    else if (ns == NS32) slice_rows_kernel<NS32><<<(rows + 7) / 8, 256, 0, st>>>(X, ld, rows, K, nullptr, planes, plane_stride, scale);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
 // columns of X and of diag(w) X from one read of X; the column maxima (bit patterns of non-negative doubles) come from the producer
-inline cudaError_t launch_slice_cols_pair(const double* X, long long ld, int n, int m, const double* w, const unsigned long long* colmaxX,
+inline cudaError_t launch_slice_cols_pair(int ns, const double* X, long long ld, int n, int m, const double* w, const unsigned long long* colmaxX,
                                           const unsigned long long* colmaxWX, int8_t* planesX, int8_t* planesWX, long long plane_stride,
                                           double* scaleX, double* scaleWX, cudaStream_t st) {
-    slice_cols_kernel<<<dim3(m / 32, n / 64), 128, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
+    const dim3 grid(m / 32, n / 64);
+    if (ns == NS64) slice_cols_kernel<NS64><<<grid, 128, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
+    else if (ns == NS32) slice_cols_kernel<NS32><<<grid, 128, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

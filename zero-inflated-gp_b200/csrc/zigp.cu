@@ -102,6 +102,7 @@ struct zigp_ctx {
     // contraction engine: 0 = DMMA (gemm_f64.cuh), 1 = fp64 on the int8 tensor cores (ozaki.cuh); dense path only
     int engine = 0;
     bool oz_ready = false;
+    int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
     // second stream for latent g (the int8 contractions of one latent overlap the fp64 / memory-bound kernels of the other)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // scratch of zigp_debug_gemm (int8 engine)
@@ -301,7 +302,7 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
         RUN(gemmM(c, L.Tt, Mp, L.P, Mp, L.Gf, Mp, L.Tt, Mp, -1.0, 1.0, Mp, Mp, Mp, st));                  // G = T^T - T^T P
         const double* src[3] = {L.T, L.R, L.Gf};
         for (int i = 0; i < 3; i++) {
-            CK(oz::launch_slice_rows(src[i], Mp, Mp, Mp, nullptr, L.ozW[i], (long long)Mp * Mp, L.ozWs[i], st));
+            CK(oz::launch_slice_rows(c->oz_ns, src[i], Mp, Mp, Mp, L.ozW[i], (long long)Mp * Mp, L.ozWs[i], st));
             c->launches++;
         }
     }
@@ -317,13 +318,13 @@ int oz_product(zigp_ctx* c, Latent& L, int wi, int rows, int tri, double* Out, d
     a.Out = Out; a.ldo = Mp; a.alpha = 1.0; a.beta = 0.0; a.rows = rows; a.cols = Mp; a.kdim = Mp; a.tri = tri;
     a.stat_sq = stat_sq; a.stat_dot = stat_dot; a.dotvec = dotvec; a.nsplit = 1;
     ProfScope ps(c, PC_GEMM, st);
-    CK(oz::launch_ozaki_gemm(A, B, a, st));
+    CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, a, st));
     c->launches++;
     return 0;
 }
 int oz_slice_in(zigp_ctx* c, Latent& L, const double* X, int rows, int Mp, cudaStream_t st) {
     ProfScope ps(c, PC_SLICE, st);
-    CK(oz::launch_slice_rows(X, Mp, rows, Mp, nullptr, L.oz_in, (long long)rows * Mp, L.oz_rs, st));
+    CK(oz::launch_slice_rows(c->oz_ns, X, Mp, rows, Mp, L.oz_in, (long long)rows * Mp, L.oz_rs, st));
     c->launches++;
     return 0;
 }
@@ -404,7 +405,7 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
         // E += Aw^T A on the int8 engine: the operands are the columns of Aw and A (k index = point), sliced transposed
         {
             ProfScope ps(c, PC_SLICE, st);
-            CK(oz::launch_slice_cols_pair(L.Ab, L.Mp, rows, L.Mp, L.gv, L.oz_colmax, L.oz_colmax + L.Mp, L.oz_colA, L.oz_colAw,
+            CK(oz::launch_slice_cols_pair(c->oz_ns, L.Ab, L.Mp, rows, L.Mp, L.gv, L.oz_colmax, L.oz_colmax + L.Mp, L.oz_colA, L.oz_colAw,
                                           (long long)L.Mp * rows, L.oz_csA, L.oz_csAw, st));
             c->launches++;
         }
@@ -414,7 +415,7 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
         a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
         a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
         ProfScope ps(c, PC_SYRK, st);
-        CK(oz::launch_ozaki_gemm(A, B, a, st));
+        CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, a, st));
         c->launches++;
         return 0;
     }
@@ -676,6 +677,9 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
         c->err = "cudaFuncSetAttribute(potrf_diag_kernel) failed";
         return fail(ZIGP_ECUDA);
     }
+    // default engine: fp64 on the int8 tensor cores; ZIGP_ENGINE=dmma (or zigp_set_engine(ctx, 0)) selects the DMMA engine
+    const char* env = getenv("ZIGP_ENGINE");
+    if (!(env && std::string(env) == "dmma") && zigp_set_engine(c, 1) != ZIGP_OK) c->engine = 0;
     *out = c;
     return ZIGP_OK;
 }
@@ -889,7 +893,7 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
     if (rows % oz::OBM || cols % oz::OBN || kdim % 128) { c->err = "zigp_debug_gemm: int8 engine needs rows % 128 == 0, cols % 64 == 0, kdim % 128 == 0"; return ZIGP_EINVAL; }
     // scratch slice buffers live in the context (grown on demand) so that repeated calls time the kernels, not cudaMalloc;
     // engine 2 = contraction only, re-using the slices of the previous engine-1 call with the same shapes
-    const size_t need_a = (size_t)oz::NSL * rows * kdim, need_b = (size_t)oz::NSL * cols * kdim;
+    const size_t need_a = (size_t)oz::NS64 * rows * kdim, need_b = (size_t)oz::NS64 * cols * kdim;
     if (need_a > c->dbg_cap_a || need_b > c->dbg_cap_b || (size_t)rows > c->dbg_cap_r || (size_t)cols > c->dbg_cap_c) {
         CK(cudaStreamSynchronize(st));
         cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
@@ -900,14 +904,14 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
         if (engine == 2) { c->err = "zigp_debug_gemm: engine 2 needs a preceding engine-1 call of the same shape"; return ZIGP_ESTATE; }
     }
     if (engine == 1) {
-        CK(oz::launch_slice_rows(In, ldi, rows, kdim, nullptr, c->dbg_pa, (long long)rows * kdim, c->dbg_sa, st));
-        CK(oz::launch_slice_rows(W, ldw, cols, kdim, nullptr, c->dbg_pb, (long long)cols * kdim, c->dbg_sb, st));
+        CK(oz::launch_slice_rows(c->oz_ns, In, ldi, rows, kdim, c->dbg_pa, (long long)rows * kdim, c->dbg_sa, st));
+        CK(oz::launch_slice_rows(c->oz_ns, W, ldw, cols, kdim, c->dbg_pb, (long long)cols * kdim, c->dbg_sb, st));
         c->launches += 2;
     }
     oz::OzOperand A{c->dbg_pa, kdim, rows, (long long)rows * kdim, c->dbg_sa}, B{c->dbg_pb, kdim, cols, (long long)cols * kdim, c->dbg_sb};
     oz::OzArgs g{};
     g.Out = Out; g.ldo = ldo; g.alpha = 1.0; g.beta = 0.0; g.rows = rows; g.cols = cols; g.kdim = kdim; g.tri = tri; g.stat_sq = stat_sq; g.nsplit = 1;
-    CK(oz::launch_ozaki_gemm(A, B, g, st));
+    CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, g, st));
     c->launches++;
     return ZIGP_OK;
 }
@@ -923,13 +927,13 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
         auto balloc = [&](void** p, size_t bytes) -> int { CK(cudaMalloc(p, bytes)); c->allocs.push_back(*p); return 0; };
         for (int l = 0; l < 2; l++) {
             Latent& L = c->lat[l];
-            RUN(balloc((void**)&L.oz_in, (size_t)oz::NSL * chunk * L.Mp));
-            RUN(balloc((void**)&L.oz_colA, (size_t)oz::NSL * chunk * L.Mp));
-            RUN(balloc((void**)&L.oz_colAw, (size_t)oz::NSL * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_in, (size_t)oz::NS64 * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_colA, (size_t)oz::NS64 * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_colAw, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colmax, (size_t)2 * L.Mp * sizeof(unsigned long long)));
             DA(L.oz_rs, chunk); DA(L.oz_csA, L.Mp); DA(L.oz_csAw, L.Mp);
             for (int i = 0; i < 3; i++) {
-                RUN(balloc((void**)&L.ozW[i], (size_t)oz::NSL * L.Mp * L.Mp));
+                RUN(balloc((void**)&L.ozW[i], (size_t)oz::NS64 * L.Mp * L.Mp));
                 DA(L.ozWs[i], L.Mp);
             }
             DA(L.Gf, (long long)L.Mp * L.Mp);
@@ -947,10 +951,18 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
 
 int zigp_get_engine(const zigp_ctx* c) { return c ? c->engine : -1; }
 
-int zigp_int8_config(int* slices, int* slice_bits, int* slice_products) {
-    if (slices) *slices = oz::NSL;
+int zigp_int8_config(const zigp_ctx* c, int* slices, int* slice_bits, int* slice_products) {
+    const int ns = c ? c->oz_ns : oz::NS64;
+    if (slices) *slices = ns;
     if (slice_bits) *slice_bits = oz::SBITS;
-    if (slice_products) *slice_products = oz::NSL * (oz::NSL + 1) / 2;
+    if (slice_products) *slice_products = ns * (ns + 1) / 2;
+    return ZIGP_OK;
+}
+
+int zigp_set_precision(zigp_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return ZIGP_EINVAL;
+    if (mode == 1 && c->engine != 1) { c->err = "zigp_set_precision: the reduced-precision mode runs on the int8 engine (zigp_set_engine(ctx, 1) first)"; return ZIGP_ESTATE; }
+    c->oz_ns = mode == 1 ? oz::NS32 : oz::NS64;
     return ZIGP_OK;
 }
 

@@ -33,7 +33,8 @@ SYMBOLS = {
     "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "zigp_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "zigp_get_engine": (C.c_int, [C.c_void_p]),
-    "zigp_int8_config": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "zigp_int8_config": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "zigp_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "zigp_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "zigp_launch_count": (C.c_int64, [C.c_void_p]),
@@ -41,13 +42,6 @@ SYMBOLS = {
     "zigp_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "zigp_flop_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
-
-
-def int8_config():
-    """(slices per operand, bits per slice, int8 slice products per fp64 product) of the int8 engine as built"""
-    a, b, c = C.c_int(), C.c_int(), C.c_int()
-    lib().zigp_int8_config(C.byref(a), C.byref(b), C.byref(c))
-    return a.value, b.value, c.value
 
 
 class ZigpError(RuntimeError):
@@ -125,6 +119,17 @@ class Context:
     PROFILE_CLASSES = ("kgen", "gemm_tn", "point", "kgrad", "syrk", "mstage_fwd", "mstage_bwd", "reduce", "slice")
 
     ENGINES = {"dmma": 0, "int8": 1}
+    PRECISIONS = {"fp64": 0, "fp32": 1}
+
+    def set_precision(self, precision):
+        """'fp64' (7 x 8-bit slices) or 'fp32' (4 x 8-bit slices: reduced precision, rel 1e-4 class) -- int8 engine only"""
+        self.call("zigp_set_precision", self.PRECISIONS[precision] if isinstance(precision, str) else int(precision))
+
+    def int8_config(self):
+        """(slices per operand, bits per slice, int8 slice products per product) of the int8 engine of this context"""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.call("zigp_int8_config", C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
     def set_engine(self, engine):
         """'dmma' (fp64 mma.sync) or 'int8' (fp64 emulated on the int8 tensor cores, csrc/ozaki.cuh)"""

@@ -81,11 +81,12 @@ class OnOffSVGP(Parameterized):
     - X is a data matrix, size N x D; Y is N x 1
     - kernf, kerng are RBF kernel objects for the f (magnitude) and g (on/off) processes
     - Zf, Zg are inducing point locations, Mf x D and Mg x D
-    Extra keyword arguments (not in the reference): device, jitter, chunk_rows, distributed, engine ('int8' | 'dmma').
+    Extra keyword arguments (not in the reference): device, jitter, chunk_rows, distributed, engine ('int8' | 'dmma'),
+    precision ('fp64' | 'fp32').
     """
 
     def __init__(self, X, Y, kernf, kerng, likelihood, Zf, Zg, mean_function=None, minibatch_size=None, name="model",
-                 device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False, engine=None):
+                 device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False, engine=None, precision=None):
         if not torch.cuda.is_available():
             raise _cabi.ZigpError("OnOffSVGP needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _cabi.lib()  # fail loudly now if the extension is missing
@@ -138,6 +139,10 @@ class OnOffSVGP(Parameterized):
         # contraction engine: "int8" = fp64 emulated on the int8 tensor cores (csrc/ozaki.cuh, the default), "dmma" = fp64 mma.sync
         self.engine = engine or os.environ.get("ZIGP_ENGINE", "int8")
         self._ctx.set_engine(self.engine)
+        # "fp64" (default; matches the reference's float64 results) or "fp32" (reduced-precision contractions, rel 1e-4 class)
+        self.precision = precision or os.environ.get("ZIGP_PRECISION", "fp64")
+        if self.precision != "fp64":
+            self._ctx.set_precision(self.precision)
         self._chunk_rows = int(chunk_rows)
         self.jitter = float(jitter)
         for p in self._theta_params():
@@ -335,6 +340,8 @@ class OnOffSVGP(Parameterized):
         self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, self.input_dim, self.jitter,
                                   getattr(self, "_chunk_rows", min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)))
         self._ctx.set_engine(getattr(self, "engine", "int8"))
+        if getattr(self, "precision", "fp64") != "fp64":
+            self._ctx.set_precision(self.precision)
         self._last_out = None
 
     # -- host-buffer entry (bench.py e2e; the call a non-torch binding would make) -----------------------------
