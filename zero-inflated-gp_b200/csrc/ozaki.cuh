@@ -253,7 +253,19 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             int rem = ct;
             for (;; tr++) { const int cnt = min(ntcg, (tr * OBM + OBM - 1) / (CL * OBN) + 1); if (rem < cnt) break; rem -= cnt; }
             tcg = rem;
-        } else { tr = ct % ntr; tcg = ct / ntr; }
+        } else {
+            // bands of `ncl` row tiles: within a band the column groups run heaviest-first with the row tile fixed per cluster, so a
+            // cluster re-uses its 128 x K slab of the row operand from L2 for all its column groups and the operand is fetched from
+            // DRAM once (profiles/ncu_int8_gemm_r01_v2.txt: 3.8 GB read per full product with the plain row-fastest order)
+            const int per_band = (int)ncl * ntcg, full_bands = ntr / (int)ncl;
+            if (ct < full_bands * per_band) {
+                const int b = ct / per_band, rem = ct % per_band;
+                tcg = rem / (int)ncl; tr = b * (int)ncl + rem % (int)ncl;
+            } else {
+                const int rows_last = ntr - full_bands * (int)ncl, rem = ct - full_bands * per_band;
+                tcg = rem / rows_last; tr = full_bands * (int)ncl + rem % rows_last;
+            }
+        }
         const int tcx = tcg * CL + (int)rank;
         const int tc = (g.tri == TRI_LOWER) ? (ntc - 1 - tcx) : tcx;
         row0 = tr * OBM; col0 = tc * OBN;
@@ -484,6 +496,7 @@ inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, O
     if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, NS, OBN, NS)) return cudaErrorInvalidValue;
     g.rscale = A.scale; g.cscale = B.scale;
     if (g.nsplit < 1) g.nsplit = 1;
+    if (g.nsplit > g.kdim / OBK) g.nsplit = std::max(1, g.kdim / OBK);     // every split owns at least one k block (short last chunk); the other split buffers stay zero
     const int ntiles = g.lower_only ? lower_tile_count(g.rows / OBM, (g.cols / OBN) / CL, CL) : (g.rows / OBM) * ((g.cols / OBN) / CL);   // cluster-tiles
     int ncl = std::max(1, (n_sms / CL) / g.nsplit);                       // persistent: at most one CTA per SM over all splits
     ncl = std::min(ncl, ntiles);
