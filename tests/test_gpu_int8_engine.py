@@ -89,3 +89,18 @@ def test_reduced_precision_mode_within_1e_4(name):
         assert err <= 1e-4 * np.linalg.norm(b) + 1e-7 * full, (k, err / np.linalg.norm(b))
         worst = max(worst, err / (np.linalg.norm(b) + 1e-300))
     print("fp32-class mode, %s: ELBO rel err %.2e, worst gradient block rel err %.2e" % (name, abs(out[0] - float(z["elbo"])) / abs(float(z["elbo"])), worst))
+
+
+def test_rank_update_split_guard_on_a_short_last_chunk():
+    """chunk of 147 456 rows -> 9 k-splits of the rank update (int32 exactness); the ragged last chunk has only 8 k blocks"""
+    N, M, D = 147456 + 100, 16, 2
+    X, Y = synth.make_data(N, D, 5)
+    p = synth.make_params(M, M, D, 5)
+    outs = {}
+    for eng in ("dmma", "int8"):
+        m = synth.build_model(X, Y, p, engine=eng, chunk_rows=147456)
+        m.build_likelihood()
+        outs[eng] = m._last_out.cpu().numpy()
+    a, b = outs["int8"], outs["dmma"]
+    assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0])
+    assert np.linalg.norm(a[4:] - b[4:]) <= 1e-10 * np.linalg.norm(b[4:])

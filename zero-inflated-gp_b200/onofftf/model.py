@@ -227,6 +227,28 @@ class OnOffKron(Parameterized):
             torch.cuda.current_stream(self.device).synchronize()
             return tuple(out9[i].reshape(-1, 1) for i in range(9))
 
+    # -- the script's optimiser set-up (scripts/onoff.py:325-350, 375-382) ------------------------------------------------
+    def make_optimizers(self, kern_param_learning_rate=1e-3, indp_param_learning_rate=1e-3):
+        """one Adam per distinct learning rate, as the script groups ``tf.trainable_variables()`` by ``var._learning_rate``:
+        kernel / likelihood parameters use ``kern_param_learning_rate`` (:88-111), inducing inputs and variational parameters
+        ``indp_param_learning_rate`` (:114-137)."""
+        kern = [p.free for p in (self.fkell + self.fkvar + self.gkell + self.gkvar + [self.noisevar]) if not p.fixed]
+        indp = [p.free for p in (self.Zf_list + self.Zg_list + [self.u_fm, self.u_fs_sqrt, self.u_gm, self.u_gs_sqrt]) if not p.fixed]
+        groups = {}
+        for lr, params in ((kern_param_learning_rate, kern), (indp_param_learning_rate, indp)):
+            groups.setdefault(float(lr), []).extend(params)
+        return [torch.optim.Adam(params, lr=lr) for lr, params in groups.items() if params]
+
+    def train_step(self, optimizers) -> float:
+        """one iteration of the script's loop: next minibatch (DataSet.next_batch), cost and gradients, one step of every Adam group"""
+        for o in optimizers:
+            o.zero_grad(set_to_none=True)
+        cost = self.cost()
+        cost.backward()
+        for o in optimizers:
+            o.step()
+        return float(cost.detach())
+
     def predict_onoff(self, Xnew):
         """the quantities onofftf/onoffpred.py:273-280 evaluates (dict of gfmean, fmean, pgmean) plus the full 9-tuple under
         'all'.  The ``gmean - 1.0`` shift of onofftf/onoffpred.py:141 is NOT applied: it is absent from the training graph."""
