@@ -706,7 +706,7 @@ int zigp_create_kron(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g, i
     int cc_major = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
     if (cc_major != 10) { c->err = "libzigp is built for sm_100a (B200) only"; return fail(ZIGP_ECUDA); }
-    long long chunk = chunk_rows > 0 ? chunk_rows : 32768;
+    long long chunk = chunk_rows > 0 ? chunk_rows : 524288;     // many small launches per chunk: large chunks amortise them (profiles/kron_chunk_r01.txt)
     c->chunk = rup(chunk, 512);
     const int Ms[2] = {Ms_f, Ms_g}, Mt[2] = {Mt_f, Mt_g};
     { int r = kron_alloc(c, Ms, Mt); if (r) return fail(r); }
