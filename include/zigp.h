@@ -52,6 +52,11 @@ typedef struct zigp_ctx zigp_ctx;
  * jitter: added to diag(Kmm) (gpflow settings.numerics.jitter_level = 1e-6 at onoffgpf/OnOffSVGP.py:96-97).
  * chunk_rows: points processed per pass of the N-stage pipeline (0 = default). */
 int zigp_create(zigp_ctx** ctx, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows);
+/* The same with the model branch chosen (onoffgpf/OnOffSVGP.py:33-34, :64-71, :88-104; gpflow conditional / gauss_kl* = onofftf/main.py:187-305):
+ * whiten = 1: whitened representation (mean = A^T q_mu, KL of gauss_kl_white*); q_full = 1: full lower-triangular q_sqrt -- theta then
+ * carries u_fs_sqrt as an Mf x Mf row-major block (lower triangle used) and u_gs_sqrt as Mg x Mg, and `out` the gradient w.r.t. the
+ * lower triangle (zeros above).  zigp_create == zigp_create_ex(..., 0, 0), the reference's live branch. */
+int zigp_create_ex(zigp_ctx** ctx, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows, int whiten, int q_full);
 int zigp_destroy(zigp_ctx* ctx);
 const char* zigp_last_error(const zigp_ctx* ctx);   /* ctx may be NULL: error of the last failed zigp_create */
 int64_t zigp_theta_len(const zigp_ctx* ctx);

@@ -169,6 +169,87 @@ __global__ void kl_kernel(const double* __restrict__ aw, const double* __restric
     if (threadIdx.x == 0) kl_out[0] = 0.5 * (t - (double)M);
 }
 
+// ---- the other (whiten, q_diag) branches of the reference model (onoffgpf/OnOffSVGP.py:64-71, 88-104): generic M-stage ----------
+// Lq (Mp x Mp, zero padding) and its transpose from theta: diag(q_sqrt) or tril(q_sqrt) (row-major M x M block)
+__global__ void build_lq_kernel(const double* __restrict__ s, int M, int Mp, int q_full, double* __restrict__ Lq, double* __restrict__ Lqt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    double v = 0.0;
+    if (i < M && j < M) {
+        if (q_full) v = (j <= i) ? s[(long long)i * M + j] : 0.0;
+        else v = (i == j) ? s[i] : 0.0;
+    }
+    Lq[(long long)i * Mp + j] = v;
+    Lqt[(long long)j * Mp + i] = v;
+}
+
+// KL = 1/2 [ |aw|^2 - M - sum log diag(Lq)^2 + |Rt|_F^2 + (whiten ? 0 : sum log L_mm^2) ]
+__global__ void kl_generic_kernel(const double* __restrict__ aw, const double* __restrict__ Lq, const double* __restrict__ Rt,
+                                  const double* __restrict__ L, int M, int Mp, int whiten, double* __restrict__ kl_out) {
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const double lq = Lq[(long long)m * Mp + m], lm = L[(long long)m * Mp + m];
+        v += aw[m] * aw[m] - log(lq * lq) + (whiten ? 0.0 : log(lm * lm));
+    }
+    for (long long e = threadIdx.x; e < (long long)Mp * Mp; e += blockDim.x) v = fma(Rt[e], Rt[e], v);
+    const double t = block_sum(v, sh);
+    if (threadIdx.x == 0) kl_out[0] = 0.5 * (t - (double)M);
+}
+
+// Sab = aw a^T - 2 E + 2 PE        (sum_n Abar_n A_n^T)
+__global__ void sab_kernel(const double* __restrict__ E, const double* __restrict__ PE, const double* __restrict__ a, const double* __restrict__ aw,
+                           int Mp, double* __restrict__ Sab) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    const long long ij = (long long)i * Mp + j;
+    Sab[ij] = aw[i] * a[j] - 2.0 * E[ij] + 2.0 * PE[ij];
+}
+
+// Tbar += (a - aw) mu^T  (optional), then zero the strict upper triangle (T is lower triangular)
+__global__ void tbar_fix_kernel(double* __restrict__ Tbar, const double* __restrict__ a, const double* __restrict__ aw, const double* __restrict__ mu,
+                                int Mp, int add_rank1) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    const long long ij = (long long)i * Mp + j;
+    double v = Tbar[ij];
+    if (add_rank1) v += (a[i] - aw[i]) * mu[j];
+    Tbar[ij] = (j <= i) ? v : 0.0;
+}
+
+// Phi = -tril(B) with the diagonal halved   (Cholesky reverse mode through T = L^-1)
+__global__ void phi_kernel(const double* __restrict__ B, int Mp, double* __restrict__ Phi) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    const long long ij = (long long)i * Mp + j;
+    Phi[ij] = (j < i) ? -B[ij] : ((j == i) ? -0.5 * B[ij] : 0.0);
+}
+
+// G = (Gp + Gp^T)/2 - (Kinv ? Kinv/2 : 0)
+__global__ void gsym_kernel(const double* __restrict__ Gp, const double* __restrict__ Kinv, int Mp, double* __restrict__ G) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    const long long ij = (long long)i * Mp + j, ji = (long long)j * Mp + i;
+    double v = 0.5 * (Gp[ij] + Gp[ji]);
+    if (Kinv) v -= 0.5 * Kinv[ij];
+    G[ij] = v;
+}
+
+__global__ void vec_sub_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
+}
+
+// dELBO/dLq: keep the lower triangle, add the -KL term + 1 / Lq_mm on the diagonal (m < M)
+__global__ void lq_grad_fix_kernel(double* __restrict__ gLq, const double* __restrict__ Lq, int M, int Mp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Mp) return;
+    const long long ij = (long long)i * Mp + j;
+    double v = (j <= i) ? gLq[ij] : 0.0;
+    if (i == j && i < M) v += 1.0 / Lq[ij];
+    gLq[ij] = v;
+}
+
 // unpack the reduced accumulator E (lower 128-tiles valid) into a full symmetric matrix
 __global__ void symmetrize_lower_kernel(const double* __restrict__ Elow, double* __restrict__ E, int Mp, int tile) {
     int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;

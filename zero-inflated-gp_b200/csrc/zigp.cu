@@ -41,6 +41,9 @@ struct Latent {
     int8_t* ozW[3] = {nullptr, nullptr, nullptr};
     double* ozWs[3] = {nullptr, nullptr, nullptr};
     double* Gf = nullptr;
+    // generic M-stage (whiten / full q_sqrt branches)
+    double *Lq = nullptr, *Lqt = nullptr, *PE = nullptr, *Sab = nullptr, *Tbar = nullptr, *RbT = nullptr, *RbTt = nullptr, *Bm = nullptr, *Phi = nullptr,
+           *Kinv = nullptr, *gLq = nullptr;
     // per-latent slice workspaces (the two latents run on two streams): row operand of the products, A / gv*A transposed
     int8_t *oz_in = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;
     double *oz_rs = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
@@ -99,6 +102,8 @@ struct zigp_ctx {
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int cat; };
     std::vector<ProfRec> prof;
+    // model branch (onoffgpf/OnOffSVGP.py:33-34): the reference's live path is whiten = false, q_full = false
+    bool whiten = false, q_full = false;
     // contraction engine: 0 = DMMA (gemm_f64.cuh), 1 = fp64 on the int8 tensor cores (ozaki.cuh); dense path only
     int engine = 0;
     bool oz_ready = false;
@@ -277,23 +282,45 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
     LAUNCHED();
     pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_mu, L.mu, M, Mp);
     LAUNCHED();
-    pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_s, L.s, M, Mp);
-    LAUNCHED();
+    if (!c->q_full) {
+        pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_s, L.s, M, Mp);
+        LAUNCHED();
+    }
     CholBufs cb{L.Lb, L.Lt, L.T, L.Tt, L.Dinv, L.Dinvt, L.Xtmp, Mp, L.nb};
     RUN(chol_inverse(c, cb, l, st));
-    colscale_kernel<<<g2, 128, 0, st>>>(L.T, L.Rt, Mp, L.s);
-    LAUNCHED();
-    transpose_kernel<<<gt, bt, 0, st>>>(L.Rt, L.R, Mp, nullptr);
-    LAUNCHED();
     const int rb = (Mp + 7) / 8;
-    rowop_kernel<<<rb, 256, 0, st>>>(L.T, nullptr, L.mu, nullptr, L.aw, Mp, 0);
-    LAUNCHED();
-    rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, L.aw, nullptr, L.beta, Mp, 0);
-    LAUNCHED();
-    rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, nullptr, nullptr, L.dK, Mp, 1);
-    LAUNCHED();
-    kl_kernel<<<1, 256, 0, st>>>(L.aw, L.s, L.dK, L.Lb, M, Mp, L.kl);
-    LAUNCHED();
+    if (c->whiten || c->q_full) {
+        // other branches of the model: alpha_w = T mu, R^T = T Lq (whiten = false)  or  alpha_w = mu, R^T = Lq (whiten = true)
+        build_lq_kernel<<<g2, 128, 0, st>>>(theta + L.off_s, M, Mp, c->q_full ? 1 : 0, L.Lq, L.Lqt);
+        LAUNCHED();
+        if (c->whiten) {
+            CK(cudaMemcpyAsync(L.Rt, L.Lq, (size_t)Mp * Mp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(L.aw, L.mu, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        } else {
+            RUN(gemmM(c, L.T, Mp, L.Lqt, Mp, L.Rt, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));
+            rowop_kernel<<<rb, 256, 0, st>>>(L.T, nullptr, L.mu, nullptr, L.aw, Mp, 0);
+            LAUNCHED();
+        }
+        transpose_kernel<<<gt, bt, 0, st>>>(L.Rt, L.R, Mp, nullptr);
+        LAUNCHED();
+        rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, L.aw, nullptr, L.beta, Mp, 0);
+        LAUNCHED();
+        kl_generic_kernel<<<1, 256, 0, st>>>(L.aw, L.Lq, L.Rt, L.Lb, M, Mp, c->whiten ? 1 : 0, L.kl);
+        LAUNCHED();
+    } else {
+        colscale_kernel<<<g2, 128, 0, st>>>(L.T, L.Rt, Mp, L.s);
+        LAUNCHED();
+        transpose_kernel<<<gt, bt, 0, st>>>(L.Rt, L.R, Mp, nullptr);
+        LAUNCHED();
+        rowop_kernel<<<rb, 256, 0, st>>>(L.T, nullptr, L.mu, nullptr, L.aw, Mp, 0);
+        LAUNCHED();
+        rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, L.aw, nullptr, L.beta, Mp, 0);
+        LAUNCHED();
+        rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, nullptr, nullptr, L.dK, Mp, 1);
+        LAUNCHED();
+        kl_kernel<<<1, 256, 0, st>>>(L.aw, L.s, L.dK, L.Lb, M, Mp, L.kl);
+        LAUNCHED();
+    }
     if (c->engine == 1) {
         // int8 engine: the backward product Y_n = T^T (I - R^T R) A_n is ONE full contraction with the explicit factor
         // G = T^T (I - P), P = R^T R (instead of V = A - R^T RA followed by Y = T^T V): two operand slicings per chunk
@@ -481,7 +508,9 @@ struct FinalArgs {
     struct Lat {
         int M, Mp; long long off_ell, off_var, off_Z, off_mu, off_s;
         const double *accV, *gZmm, *pell, *pvar, *gmu, *dE, *dK, *s, *kl;
+        const double* gLq;       // generic branches: dELBO/dLq (Mp x Mp); null on the reference's live branch
     } lat[2];
+    int q_full;
 };
 
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs f) {
@@ -508,10 +537,22 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs f) {
             for (int m = threadIdx.x; m < L.M; m += blockDim.x)
                 grad[L.off_Z + (long long)m * D + d] = S1[(long long)d * L.Mp + m] / (ell * ell) + L.gZmm[m * D + d];
         }
-        for (int m = threadIdx.x; m < L.M; m += blockDim.x) {
-            const double s = L.s[m];
-            grad[L.off_mu + m] = L.gmu[m];
-            grad[L.off_s + m] = 2.0 * s * L.dE[m] + 1.0 / s - s * L.dK[m];
+        if (L.gLq) {
+            for (int m = threadIdx.x; m < L.M; m += blockDim.x) grad[L.off_mu + m] = L.gmu[m];
+            if (f.q_full) {
+                for (int e = threadIdx.x; e < L.M * L.M; e += blockDim.x) {
+                    const int i = e / L.M, j = e % L.M;
+                    grad[L.off_s + e] = (j <= i) ? L.gLq[(long long)i * L.Mp + j] : 0.0;
+                }
+            } else {
+                for (int m = threadIdx.x; m < L.M; m += blockDim.x) grad[L.off_s + m] = L.gLq[(long long)m * L.Mp + m];
+            }
+        } else {
+            for (int m = threadIdx.x; m < L.M; m += blockDim.x) {
+                const double s = L.s[m];
+                grad[L.off_mu + m] = L.gmu[m];
+                grad[L.off_s + m] = 2.0 * s * L.dE[m] + 1.0 / s - s * L.dK[m];
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -524,12 +565,57 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalArgs f) {
     }
 }
 
+// M-stage backward of the whiten / full-q_sqrt branches (tests/algo_model_variants.py is the float64 model of exactly this):
+//   Sab = aw a^T - 2 E + 2 P E ;  Tbar = Sab L^T (+ (a - aw) mu^T + RbT Lq^T) ;  RbT = 2 E Rt - Rt ;  dLq = tril(T^T RbT | RbT) + 1/diag
+//   B = tril(Tbar) T^T ;  Phi = -tril(B), diagonal halved ;  G = sym(T^T Phi T) (- K^-1 / 2)
+int finish_generic_latent(zigp_ctx* c, Latent& L, const double* theta, const double* a, cudaStream_t st) {
+    const int Mp = L.Mp;
+    dim3 g2((Mp + 127) / 128, Mp);
+    dim3 gt(Mp / 32, Mp / 32), bt(32, 8);
+    RUN(gemmM(c, L.Rt, Mp, L.Rt, Mp, L.P, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));                 // P = R^T R
+    RUN(gemmM(c, L.P, Mp, L.E, Mp, L.PE, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));                  // P E  (E symmetric)
+    sab_kernel<<<g2, 128, 0, st>>>(L.E, L.PE, a, L.aw, Mp, L.Sab);
+    LAUNCHED();
+    RUN(gemmM(c, L.Sab, Mp, L.Lb, Mp, L.Tbar, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));             // Sab L^T
+    RUN(gemmM(c, L.E, Mp, L.R, Mp, L.RbT, Mp, L.Rt, Mp, 2.0, -1.0, Mp, Mp, Mp, st));                  // RbT = 2 E Rt - Rt
+    const int rb = (Mp + 7) / 8;
+    if (c->whiten) {
+        vec_sub_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(a, L.aw, L.gmu, Mp);                          // d mu = a - aw
+        LAUNCHED();
+        CK(cudaMemcpyAsync(L.gLq, L.RbT, (size_t)Mp * Mp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        tbar_fix_kernel<<<g2, 128, 0, st>>>(L.Tbar, a, L.aw, L.mu, Mp, 0);
+        LAUNCHED();
+    } else {
+        rowop_kernel<<<rb, 256, 0, st>>>(L.Tt, nullptr, a, L.aw, L.gmu, Mp, 0);                        // d mu = T^T (a - aw)
+        LAUNCHED();
+        RUN(gemmM(c, L.RbT, Mp, L.Lq, Mp, L.Tbar, Mp, L.Tbar, Mp, 1.0, 1.0, Mp, Mp, Mp, st));          // Tbar += RbT Lq^T
+        tbar_fix_kernel<<<g2, 128, 0, st>>>(L.Tbar, a, L.aw, L.mu, Mp, 1);                             // += (a - aw) mu^T, lower part
+        LAUNCHED();
+        transpose_kernel<<<gt, bt, 0, st>>>(L.RbT, L.RbTt, Mp, nullptr);
+        LAUNCHED();
+        RUN(gemmM(c, L.Tt, Mp, L.RbTt, Mp, L.gLq, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));          // T^T RbT
+    }
+    lq_grad_fix_kernel<<<g2, 128, 0, st>>>(L.gLq, L.Lq, L.M, Mp);                                      // lower part + 1 / diag(Lq)
+    LAUNCHED();
+    RUN(gemmM(c, L.Tbar, Mp, L.T, Mp, L.Bm, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));               // B = tril(Tbar) T^T
+    phi_kernel<<<g2, 128, 0, st>>>(L.Bm, Mp, L.Phi);
+    LAUNCHED();
+    RUN(gemmM(c, L.Tt, Mp, L.Phi, Mp, L.Ut, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));               // (Phi T)^T
+    RUN(gemmM(c, L.Tt, Mp, L.Ut, Mp, L.Hs, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));                // T^T Phi T
+    if (!c->whiten) RUN(gemmM(c, L.Tt, Mp, L.Tt, Mp, L.Kinv, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));   // K^-1 = T^T T
+    gsym_kernel<<<g2, 128, 0, st>>>(L.Hs, c->whiten ? nullptr : L.Kinv, Mp, L.G);
+    LAUNCHED();
+    kmm_grad_kernel<<<L.M, 128, 0, st>>>(L.G, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, L.M, c->D, Mp, L.gZmm, L.pell, L.pvar);
+    LAUNCHED();
+    return 0;
+}
+
 int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
     CK(cudaSetDevice(c->device));
     ProfScope ps(c, PC_MBWD, st);
     const int D = c->D;
     FinalArgs f{};
-    f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.D = D;
+    f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.D = D; f.q_full = c->q_full ? 1 : 0;
     for (int l = 0; l < 2; l++) {
         Latent& L = c->lat[l];
         const int Mp = L.Mp;
@@ -537,6 +623,14 @@ int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
         const double* a = L.accV + Mp;     // second row of the vector block
         symmetrize_lower_kernel<<<g2, 128, 0, st>>>(L.accE, L.E, Mp, BMN);
         LAUNCHED();
+        if (c->whiten || c->q_full) {
+            RUN(finish_generic_latent(c, L, theta, a, st));
+            FinalArgs::Lat& q = f.lat[l];
+            q.M = L.M; q.Mp = Mp; q.off_ell = L.off_ell; q.off_var = L.off_var; q.off_Z = L.off_Z; q.off_mu = L.off_mu; q.off_s = L.off_s;
+            q.accV = L.accV; q.gZmm = L.gZmm; q.pell = L.pell; q.pvar = L.pvar; q.gmu = L.gmu; q.dE = L.dE; q.dK = L.dK; q.s = L.s; q.kl = L.kl;
+            q.gLq = L.gLq;
+            continue;
+        }
         RUN(gemmM(c, L.Rt, Mp, L.Rt, Mp, L.P, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));       // P = R^T R
         RUN(gemmM(c, L.E, Mp, L.P, Mp, L.EP, Mp, nullptr, 0, 1.0, 0.0, Mp, Mp, Mp, st));          // EP
         hs_kernel<<<g2, 128, 0, st>>>(L.E, L.EP, L.P, a, L.aw, Mp, L.Hs);
@@ -586,6 +680,10 @@ void not_pd_message(zigp_ctx* c, long long info) {
 extern "C" {
 
 int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows) {
+    return zigp_create_ex(out, device, Mf, Mg, D, jitter, chunk_rows, 0, 0);
+}
+
+int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows, int whiten, int q_full) {
     if (!out) return ZIGP_EINVAL;
     *out = nullptr;
     if (Mf <= 0 || Mg <= 0 || D <= 0 || D > ZIGP_MAX_D || !(jitter >= 0.0) || Mf >= (1 << 20) || Mg >= (1 << 20)) {
@@ -599,7 +697,7 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
         return ZIGP_ECUDA;
     }
     zigp_ctx* c = new zigp_ctx();
-    c->device = device; c->D = D; c->jitter = jitter;
+    c->device = device; c->D = D; c->jitter = jitter; c->whiten = whiten != 0; c->q_full = q_full != 0;
     auto fail = [&](int code) { g_create_error = c->err; zigp_destroy(c); return code; };
     if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(ZIGP_ECUDA); }
     int cc_major = 0;
@@ -611,7 +709,7 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
     c->lat[0].off_ell = 0; c->lat[0].off_var = D; c->lat[1].off_ell = D + 1; c->lat[1].off_var = 2 * D + 1;
     for (int l = 0; l < 2; l++) { c->lat[l].M = Ms[l]; c->lat[l].off_Z = off; off += (long long)Ms[l] * D; }
     for (int l = 0; l < 2; l++) { c->lat[l].off_mu = off; off += Ms[l]; }
-    for (int l = 0; l < 2; l++) { c->lat[l].off_s = off; off += Ms[l]; }
+    for (int l = 0; l < 2; l++) { c->lat[l].off_s = off; off += c->q_full ? (long long)Ms[l] * Ms[l] : Ms[l]; }
     c->theta_len = off;
 
     long long chunk = chunk_rows > 0 ? chunk_rows : 32768;
@@ -652,6 +750,10 @@ int zigp_create(zigp_ctx** out, int device, int Mf, int Mg, int D, double jitter
             DA(L.mu, Mp); DA(L.s, Mp); DA(L.aw, Mp); DA(L.beta, Mp); DA(L.dK, Mp); DA(L.kl, 2);
             DA(L.E, MM); DA(L.P, MM); DA(L.EP, MM); DA(L.Hs, MM); DA(L.Ut, MM); DA(L.G, MM); DA(L.ETt, MM);
             DA(L.dE, Mp); DA(L.gmu, Mp); DA(L.gZmm, Mp * D); DA(L.pell, Mp * D); DA(L.pvar, Mp);
+            if (c->whiten || c->q_full) {
+                DA(L.Lq, MM); DA(L.Lqt, MM); DA(L.PE, MM); DA(L.Sab, MM); DA(L.Tbar, MM); DA(L.RbT, MM); DA(L.RbTt, MM); DA(L.Bm, MM); DA(L.Phi, MM);
+                DA(L.Kinv, MM); DA(L.gLq, MM);
+            }
             DA(L.Kb, chunk * Mp); DA(L.Ab, chunk * Mp); DA(L.RAb, chunk * Mp); DA(L.Vb, chunk * Mp);
             DA(L.sqA, (long long)L.ntc * chunk); DA(L.dotA, (long long)L.ntc * chunk); DA(L.sqRA, (long long)L.ntc * chunk);
             DA(L.mean, chunk); DA(L.vr, chunk); DA(L.gm, chunk); DA(L.gv, chunk);

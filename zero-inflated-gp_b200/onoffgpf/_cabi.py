@@ -16,6 +16,7 @@ _lib = None
 SYMBOLS = {
     # name: (restype, argtypes)
     "zigp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
+    "zigp_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int]),
     "zigp_create_kron": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
     "zigp_destroy": (C.c_int, [C.c_void_p]),
     "zigp_last_error": (C.c_char_p, [C.c_void_p]),
@@ -80,11 +81,11 @@ def check(ctx, rc):
 class Context:
     """Owns one zigp_ctx (one GPU)."""
 
-    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0, kron=None):
+    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0, kron=None, whiten=False, q_full=False):
         """dense context, or with kron=(Ms_f, Mt_f, Ms_g, Mt_g, Ds, Dt) the Kronecker variant (zigp_create_kron)"""
         self._h = C.c_void_p()
         if kron is None:
-            rc = lib().zigp_create(C.byref(self._h), int(device), int(Mf), int(Mg), int(D), float(jitter), int(chunk_rows))
+            rc = lib().zigp_create_ex(C.byref(self._h), int(device), int(Mf), int(Mg), int(D), float(jitter), int(chunk_rows), int(bool(whiten)), int(bool(q_full)))
         else:
             rc = lib().zigp_create_kron(C.byref(self._h), int(device), *[int(v) for v in kron], float(jitter), int(chunk_rows))
         if rc != 0:

@@ -21,7 +21,7 @@ import torch
 
 from . import _cabi, parallel
 from .likelihood import OnOffLikelihood
-from .param import DTYPE, DataHolder, Param, Parameterized, positive
+from .param import DTYPE, DataHolder, LowerTriangular, Param, Parameterized, positive
 
 JITTER_LEVEL = 1e-6          # gpflow 0.4 settings.numerics.jitter_level (onoffgpf/OnOffSVGP.py:96-97)
 DEFAULT_CHUNK_ROWS = 65536
@@ -86,7 +86,8 @@ class OnOffSVGP(Parameterized):
     """
 
     def __init__(self, X, Y, kernf, kerng, likelihood, Zf, Zg, mean_function=None, minibatch_size=None, name="model",
-                 device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False, engine=None, precision=None):
+                 device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False, engine=None, precision=None,
+                 whiten=False, q_diag=True):
         if not torch.cuda.is_available():
             raise _cabi.ZigpError("OnOffSVGP needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _cabi.lib()  # fail loudly now if the extension is missing
@@ -95,8 +96,10 @@ class OnOffSVGP(Parameterized):
         if not isinstance(self.mean_function, Zero):
             raise NotImplementedError("only the Zero mean function is supported (the reference uses no other)")
         self.kernf, self.kerng, self.likelihood = kernf, kerng, likelihood
-        self.whiten = False      # onoffgpf/OnOffSVGP.py:33
-        self.q_diag = True       # onoffgpf/OnOffSVGP.py:34
+        # the reference hard-codes whiten = False, q_diag = True (onoffgpf/OnOffSVGP.py:33-34) and keeps the other branches as code
+        # (:64-71, :88-104); here they are constructor arguments
+        self.whiten = bool(whiten)
+        self.q_diag = bool(q_diag)
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
         Y = np.ascontiguousarray(np.asarray(Y, dtype=np.float64))
         if X.ndim != 2 or Y.ndim != 2 or Y.shape[1] != 1 or Y.shape[0] != X.shape[0]:
@@ -126,8 +129,12 @@ class OnOffSVGP(Parameterized):
         self.Zf, self.Zg = Param(Zf), Param(Zg)
         self.u_fm = Param(np.random.randn(self.num_inducing_f, self.num_latent) * 0.01)   # :56
         self.u_gm = Param(np.random.randn(self.num_inducing_g, self.num_latent) * 0.01)   # :57
-        self.u_fs_sqrt = Param(np.ones((self.num_inducing_f, self.num_latent)), positive)  # :60
-        self.u_gs_sqrt = Param(np.ones((self.num_inducing_g, self.num_latent)), positive)  # :62
+        if self.q_diag:
+            self.u_fs_sqrt = Param(np.ones((self.num_inducing_f, self.num_latent)), positive)  # :60
+            self.u_gs_sqrt = Param(np.ones((self.num_inducing_g, self.num_latent)), positive)  # :62
+        else:
+            self.u_fs_sqrt = Param(np.eye(self.num_inducing_f)[:, :, None], LowerTriangular(self.num_inducing_f))   # :65-67
+            self.u_gs_sqrt = Param(np.eye(self.num_inducing_g)[:, :, None], LowerTriangular(self.num_inducing_g))   # :69-71
 
         self._X_dev = torch.as_tensor(X).to(self.device)
         self._Y_dev = torch.as_tensor(Y).reshape(-1).to(self.device)
@@ -135,7 +142,8 @@ class OnOffSVGP(Parameterized):
         rows = min(self.minibatch_size, n_local)
         if chunk_rows is None:
             chunk_rows = min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)
-        self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, D, jitter, chunk_rows)
+        self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, D, jitter, chunk_rows,
+                                  whiten=self.whiten, q_full=not self.q_diag)
         # contraction engine: "int8" = fp64 emulated on the int8 tensor cores (csrc/ozaki.cuh, the default), "dmma" = fp64 mma.sync
         self.engine = engine or os.environ.get("ZIGP_ENGINE", "int8")
         self._ctx.set_engine(self.engine)
@@ -338,7 +346,8 @@ class OnOffSVGP(Parameterized):
         self._Xb, self._Yb = self._X_dev, self._Y_dev
         rows = min(self.minibatch_size, self.num_data_local)
         self._ctx = _cabi.Context(self.device.index or 0, self.num_inducing_f, self.num_inducing_g, self.input_dim, self.jitter,
-                                  getattr(self, "_chunk_rows", min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)))
+                                  getattr(self, "_chunk_rows", min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)),
+                                  whiten=getattr(self, "whiten", False), q_full=not getattr(self, "q_diag", True))
         self._ctx.set_engine(getattr(self, "engine", "int8"))
         if getattr(self, "precision", "fp64") != "fp64":
             self._ctx.set_precision(self.precision)

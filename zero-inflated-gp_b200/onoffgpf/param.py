@@ -42,12 +42,35 @@ class Log1pe:
 positive = Log1pe()
 
 
+class LowerTriangular:
+    """gpflow.transforms.LowerTriangular(N): the free state is the vector of the N (N + 1) / 2 entries of the lower triangle (row by
+    row), the constrained value the N x N x 1 array with zeros above the diagonal (onoffgpf/OnOffSVGP.py:64-71)."""
+
+    def __init__(self, N):
+        self.N = int(N)
+        self._idx = torch.tril_indices(self.N, self.N)
+
+    def forward(self, x):
+        L = torch.zeros((self.N, self.N), dtype=x.dtype, device=x.device)
+        idx = self._idx.to(x.device)
+        L = L.index_put((idx[0], idx[1]), x.reshape(-1))
+        return L.unsqueeze(-1)
+
+    def backward(self, y):
+        y = y.reshape(self.N, self.N, -1)[:, :, 0]
+        return y[self._idx[0], self._idx[1]]
+
+    def __repr__(self):
+        return "LoTri"
+
+
+
 class Param:
     def __init__(self, array, transform=None):
         self.transform = transform or Identity()
         arr = torch.as_tensor(np.atleast_1d(np.asarray(array, dtype=np.float64))).clone()
         self._shape = tuple(arr.shape)
-        self.free = self.transform.backward(arr).detach().clone().requires_grad_(True)
+        self.free = self.transform.backward(arr).detach().clone().contiguous().requires_grad_(True)
         self._fixed = False
 
     # -- gpflow surface -------------------------------------------------------------------------------------
@@ -75,7 +98,7 @@ class Param:
     def assign(self, array):
         arr = torch.as_tensor(np.broadcast_to(np.asarray(array, dtype=np.float64), self._shape).copy())
         with torch.no_grad():
-            self.free.copy_(self.transform.backward(arr).to(self.free.device))
+            self.free.copy_(self.transform.backward(arr).to(self.free.device).reshape(self.free.shape))
 
     # -- torch surface --------------------------------------------------------------------------------------
     def constrained(self) -> torch.Tensor:
