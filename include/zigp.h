@@ -72,6 +72,13 @@ int64_t zigp_theta_len(const zigp_ctx* ctx);
  *   out[3] info: k > 0 -> pivot (k-1) % 2^20 of factor ((k-1) >> 20) & 1 (0 = space, 1 = time) of latent (k-1) >> 21. */
 int zigp_create_kron(zigp_ctx** ctx, int device, int Ms_f, int Mt_f, int Ms_g, int Mt_g, int Ds, int Dt, double jitter, int64_t chunk_rows);
 
+/* The same Kronecker machinery with the likelihood of the reference's comparison models: model 0 = on/off (above);
+ * 1 = SVGP regression, one latent, Gaussian likelihood (scripts/svgp.py:111-133, 201-225); 2 = classifier, one latent, probit Bernoulli
+ * with the squashed CDF (scripts/classifier.py:116-142, 210-217; targets 1.0 / 0.0).  For models 1 and 2 only latent f exists:
+ *   theta = [ell_s[Ds], var_s, ell_t[Dt], var_t], noise_var (unused by model 2), Zf_s, Zf_t, u_fm, u_fs_sqrt ;
+ * predict fills rows (fmean, fvar) resp. (p, p - p^2, fmean, fvar) of the 9 x n block. */
+int zigp_create_kron_ex(zigp_ctx** ctx, int device, int Ms_f, int Mt_f, int Ms_g, int Mt_g, int Ds, int Dt, double jitter, int64_t chunk_rows, int model);
+
 /* Attach this rank's shard of the minibatch: X (n_local x D), Y (n_local).  scale = num_data / global batch size
  * (onoffgpf/OnOffSVGP.py:119-120).  Device pointers are borrowed until the next set_data / destroy. */
 int zigp_set_data_dev(zigp_ctx* ctx, const double* X_dev, const double* Y_dev, int64_t n_local, double scale);

@@ -199,3 +199,47 @@ def predict_onoff(Xnew, params, jitter=JITTER_KRON):
     with torch.no_grad():
         out = build_predict(torch.as_tensor(Xnew, dtype=DTYPE), params, jitter)
     return tuple(o.reshape(-1, 1).numpy() for o in out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The reference's single-latent comparison models on the same Kronecker conditional
+#   SVGP regression ...... scripts/svgp.py:111-133 (build_prior_kl, build_predict), :201-225 (Gaussian variational expectation, cost)
+#   probit classifier .... scripts/classifier.py:116-142 (build_prior_kl, build_predict), :210-217 (bernoulli / probit), cost likewise
+# ---------------------------------------------------------------------------------------------------------------------------
+SINGLE_NAMES = ("fkell_s", "fkvar_s", "fkell_t", "fkvar_t", "noisevar", "Zf_s", "Zf_t", "u_fm", "u_fs_sqrt")
+
+
+def single_build_likelihood(X, Y, p, model, num_data=None, jitter=JITTER_KRON, return_parts=False):
+    """model 'svgp': sum(-1/2 log 2pi - 1/2 log noise - 1/2 ((y - fmean)^2 + fvar) / noise) * scale - kl      (scripts/svgp.py:201-225)
+       model 'classifier': p = probit(fmean / sqrt(1 + fvar)); sum(log(where(y == 1, p, 1 - p))) * scale - kl   (scripts/classifier.py:139-141, 210-217)"""
+    ells, variances, Zl = _factors(p, "f")
+    Kmm = [rbf_K(Zl[i], None, ells[i], variances[i]) + torch.eye(Zl[i].shape[0], dtype=DTYPE) * jitter for i in range(2)]
+    kl = gauss_kl_kron(p["u_fm"], p["u_fs_sqrt"], Kmm)
+    fmean, fvar = kron_inf(X, ells, variances, Zl, p["u_fm"], p["u_fs_sqrt"], jitter)
+    if model == "svgp":
+        var_exp = torch.sum(-0.5 * np.log(2 * np.pi) - 0.5 * torch.log(p["noisevar"]) - 0.5 * (torch.square(Y - fmean) + fvar) / p["noisevar"])
+    else:
+        pf = 0.5 * (1.0 + torch.erf(fmean / torch.sqrt(1 + fvar) / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+        var_exp = torch.sum(torch.log(torch.where(Y == 1, pf, 1 - pf)))
+    num_data = X.shape[0] if num_data is None else num_data
+    elbo = var_exp * (float(num_data) / float(X.shape[0])) - kl
+    return (elbo, var_exp, kl) if return_parts else elbo
+
+
+def single_predict(Xnew, p, model, jitter=JITTER_KRON):
+    ells, variances, Zl = _factors(p, "f")
+    with torch.no_grad():
+        fmean, fvar = kron_inf(torch.as_tensor(Xnew, dtype=DTYPE), ells, variances, Zl, p["u_fm"], p["u_fs_sqrt"], jitter)
+        if model == "svgp":
+            return fmean.numpy(), fvar.numpy()
+        pf = 0.5 * (1.0 + torch.erf(fmean / torch.sqrt(1 + fvar) / np.sqrt(2.0))) * (1 - 2e-3) + 1e-3
+        return pf.numpy(), (pf - pf * pf).numpy(), fmean.numpy(), fvar.numpy()
+
+
+def single_elbo_and_grads(X, Y, params, model, num_data=None, jitter=JITTER_KRON):
+    X = torch.as_tensor(X, dtype=DTYPE); Y = torch.as_tensor(Y, dtype=DTYPE).reshape(-1, 1)
+    leaves = {k: params[k].detach().clone().to(DTYPE).requires_grad_(True) for k in SINGLE_NAMES}
+    elbo, data_term, kl = single_build_likelihood(X, Y, leaves, model, num_data, jitter, return_parts=True)
+    grads = torch.autograd.grad(elbo, [leaves[k] for k in SINGLE_NAMES], allow_unused=True)
+    g = {k: (torch.zeros_like(leaves[k]) if gi is None else gi.detach()) for k, gi in zip(SINGLE_NAMES, grads)}
+    return float(elbo.detach()), float(data_term.detach()), float(kl.detach()), g

@@ -151,3 +151,38 @@ def test_kron_adam_training_loop_on_reference_data():
     opts = mb.make_optimizers(kern_param_learning_rate=1e-3, indp_param_learning_rate=2e-3)
     assert len(opts) == 2
     assert all(np.isfinite(mb.train_step(opts)) for _ in range(10))
+
+
+@pytest.mark.parametrize("model", ["svgp", "classifier"])
+def test_kron_comparison_models_against_oracle(model):
+    """the single-latent comparison models of scripts/svgp.py and scripts/classifier.py on the shared Kronecker conditional"""
+    from onofftf import KronClassifier, KronSVGP
+    N, Ms, Mt = 1200, 9, 14
+    X, Y = synth.make_data(N, 3, seed=31)
+    if model == "classifier":
+        Y = (Y > 0).astype(np.float64)                       # scripts/classifier.py:44
+    p = synth.make_kron_params(Ms, Mt, 2, 1, seed=31)
+    rng = np.random.default_rng(31)
+    p["u_fm"] = 0.3 * rng.standard_normal((Ms * Mt, 1)); p["u_fs_sqrt"] = 0.5 + rng.random((Ms * Mt, 1))
+    q = kro.as_params(**p)
+    e, dt, kl, g = kro.single_elbo_and_grads(X, Y, q, model, num_data=2 * N)
+    cls = KronSVGP if model == "svgp" else KronClassifier
+    m = cls(X, Y, [p["Zf_s"], p["Zf_t"]], [p["fkell_s"], p["fkell_t"]], [p["fkvar_s"], p["fkvar_t"]], noisevar=p["noisevar"], u_fm=p["u_fm"], u_fs_sqrt=p["u_fs_sqrt"])
+    m.num_data = 2 * N
+    elbo = m.build_likelihood()
+    torch.autograd.grad(elbo, m.trainable_tensors(), allow_unused=True)
+    out = m._last_out.cpu().numpy()
+    assert out[3] == 0
+    for got, ref in ((out[0], e), (out[1], dt), (out[2], kl)):
+        assert abs(got - ref) <= 1e-10 * abs(ref), (got, ref)
+    o = 4
+    full = np.sqrt(sum(float(torch.sum(v * v)) for v in g.values()))
+    for k in kro.SINGLE_NAMES:
+        b = g[k].numpy().reshape(-1)
+        a = out[o:o + b.size]; o += b.size
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b) + 1e-11 * full, (k, np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+    assert o == len(out)
+    ref = kro.single_predict(X[:40], q, model)
+    got = m.build_predict(X[:40])
+    assert np.allclose(got[0].cpu().numpy(), ref[0], rtol=1e-9, atol=1e-11) and np.allclose(got[1].cpu().numpy(), ref[1], rtol=1e-9, atol=1e-11)
+    assert abs(float(m.build_prior_kl()) - kl) <= 1e-10 * abs(kl)

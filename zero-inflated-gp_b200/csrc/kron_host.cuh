@@ -86,11 +86,12 @@ int kron_chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X,
 
 int kron_point(zigp_ctx* c, const double* theta, const double* Y, long long n0, int nvalid, int rows, cudaStream_t st) {
     PointArgs p{};
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         p.mean[l] = L.mean; p.vr[l] = L.vr; p.gm[l] = L.gm; p.gv[l] = L.gv;
     }
     p.precomputed = 1;
+    p.lik = c->lik;
     p.noise = theta + c->off_noise;
     p.Y = Y; p.n0 = n0; p.nvalid = Y ? nvalid : 0; p.rows = rows; p.scale = c->scale; p.partial = c->pt_partial;
     ProfScope ps(c, PC_POINT, st);
@@ -141,7 +142,7 @@ int kron_accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     CK(cudaMemsetAsync(c->pt_partial, 0, (size_t)c->pt_slots * 4 * sizeof(double), st));
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         const long long qn = (long long)L.f[0].Mp * L.f[1].Mp;
         CK(cudaMemsetAsync(L.Qbar_splits, 0, (size_t)L.nsplit * qn * sizeof(double), st));
@@ -156,14 +157,14 @@ int kron_accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
         const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
         const int rows = (int)rup(nvalid, 512);
-        for (int l = 0; l < 2; l++) RUN(kron_chunk_forward(c, l, theta, c->X, n0, nvalid, rows, st));
+        for (int l = 0; l < c->nlat; l++) RUN(kron_chunk_forward(c, l, theta, c->X, n0, nvalid, rows, st));
         RUN(kron_point(c, theta, c->Y, n0, nvalid, rows, st));
-        for (int l = 0; l < 2; l++) RUN(kron_chunk_backward(c, l, theta, n0, nvalid, rows, st));
+        for (int l = 0; l < c->nlat; l++) RUN(kron_chunk_backward(c, l, theta, n0, nvalid, rows, st));
     }
     ProfScope psr(c, PC_REDUCE, st);
     reduce_slots_kernel<<<1, 32, 0, st>>>(c->pt_partial, 4, c->pt_slots, c->accum, 4);
     LAUNCHED();
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         const long long qn = (long long)L.f[0].Mp * L.f[1].Mp;
         reduce_slots_kernel<<<(unsigned)((qn + 255) / 256), 256, 0, st>>>(L.Qbar_splits, qn, L.nsplit, L.accQbar, qn);
@@ -187,12 +188,13 @@ struct KronFinalArgs {
     double scale; long long off_noise;
     struct Fac { int M, Mp, D; long long off_ell, off_var, off_Z; const double *accV, *gZ, *pell, *pvar, *d; };
     struct Lat { int Ms, Mt, Msp, Mtp; long long off_mu, off_s; const double *Qbar, *S2bar, *Ymu, *kl; Fac f[2]; } lat[2];
+    int nlat;
 };
 
 __global__ void __launch_bounds__(256) kron_finalize_kernel(const KronFinalArgs f) {
     __shared__ double sh[32];
     double* grad = f.out + ZIGP_OUT_HEADER;
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < f.nlat; l++) {
         const KronFinalArgs::Lat& L = f.lat[l];
         for (int p = 0; p < 2; p++) {
             const KronFinalArgs::Fac& F = L.f[p];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(256) kron_finalize_kernel(const KronFinalArgs 
         }
     }
     if (threadIdx.x == 0) {
-        const double kl = f.lat[0].kl[0] + f.lat[1].kl[0];
+        const double kl = f.lat[0].kl[0] + (f.nlat > 1 ? f.lat[1].kl[0] : 0.0);
         f.out[0] = f.scale * f.accum[0] - kl;
         f.out[1] = f.accum[0];
         f.out[2] = kl;
@@ -239,8 +241,8 @@ int kron_finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) 
     CK(cudaSetDevice(c->device));
     ProfScope ps(c, PC_MBWD, st);
     KronFinalArgs f{};
-    f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.off_noise = c->off_noise;
-    for (int l = 0; l < 2; l++) {
+    f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.off_noise = c->off_noise; f.nlat = c->nlat;
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         KFactor &S = L.f[0], &T = L.f[1];
         const int Msp = S.Mp, Mtp = T.Mp;
@@ -282,8 +284,8 @@ int kron_finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) 
 int kron_prior_kl(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
-    for (int l = 0; l < 2; l++) RUN(kron_mstage_forward(c, l, theta, st));
-    kl_out_kernel<<<1, 1, 0, st>>>(c->klat[0].kl, c->klat[1].kl, c->info, out);
+    for (int l = 0; l < c->nlat; l++) RUN(kron_mstage_forward(c, l, theta, st));
+    kl_out_kernel<<<1, 1, 0, st>>>(c->klat[0].kl, c->nlat > 1 ? c->klat[1].kl : c->zero2, c->info, out);
     LAUNCHED();
     return ZIGP_OK;
 }
@@ -291,12 +293,15 @@ int kron_prior_kl(zigp_ctx* c, const double* theta, double* out, cudaStream_t st
 int kron_predict(zigp_ctx* c, const double* theta, const double* Xnew, long long n_new, double* out9, cudaStream_t st) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
-    for (int l = 0; l < 2; l++) RUN(kron_mstage_forward(c, l, theta, st));
+    for (int l = 0; l < c->nlat; l++) RUN(kron_mstage_forward(c, l, theta, st));
     for (long long n0 = 0; n0 < n_new; n0 += c->chunk) {
         const int nvalid = (int)std::min<long long>(c->chunk, n_new - n0);
         const int rows = (int)rup(nvalid, 512);
-        for (int l = 0; l < 2; l++) RUN(kron_chunk_forward(c, l, theta, Xnew, n0, nvalid, rows, st));
-        predict_kernel<<<(nvalid + 255) / 256, 256, 0, st>>>(c->klat[0].mean, c->klat[0].vr, c->klat[1].mean, c->klat[1].vr, nvalid, n0, n_new, out9);
+        for (int l = 0; l < c->nlat; l++) RUN(kron_chunk_forward(c, l, theta, Xnew, n0, nvalid, rows, st));
+        if (c->nlat > 1)
+            predict_kernel<<<(nvalid + 255) / 256, 256, 0, st>>>(c->klat[0].mean, c->klat[0].vr, c->klat[1].mean, c->klat[1].vr, nvalid, n0, n_new, out9);
+        else
+            predict1_kernel<<<(nvalid + 255) / 256, 256, 0, st>>>(c->klat[0].mean, c->klat[0].vr, nvalid, n0, n_new, c->lik, out9);
         LAUNCHED();
     }
     return ZIGP_OK;
@@ -306,7 +311,7 @@ int kron_predict(zigp_ctx* c, const double* theta, const double* Xnew, long long
 int kron_alloc(zigp_ctx* c, const int Ms[2], const int Mt[2]) {
     const int Ds = c->Ds, Dt = c->Dt;
     long long off = 0;
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         L.Ms = Ms[l]; L.Mt = Mt[l];
         KFactor &S = L.f[0], &T = L.f[1];
@@ -315,20 +320,20 @@ int kron_alloc(zigp_ctx* c, const int Ms[2], const int Mt[2]) {
         T.off_ell = off; off += Dt; T.off_var = off; off += 1;
     }
     c->off_noise = off; off += 1;
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         L.f[0].off_Z = off; off += (long long)L.Ms * Ds;
         L.f[1].off_Z = off; off += (long long)L.Mt * Dt;
     }
-    for (int l = 0; l < 2; l++) { c->klat[l].off_mu = off; off += (long long)c->klat[l].Ms * c->klat[l].Mt; }
-    for (int l = 0; l < 2; l++) { c->klat[l].off_s = off; off += (long long)c->klat[l].Ms * c->klat[l].Mt; }
+    for (int l = 0; l < c->nlat; l++) { c->klat[l].off_mu = off; off += (long long)c->klat[l].Ms * c->klat[l].Mt; }
+    for (int l = 0; l < c->nlat; l++) { c->klat[l].off_s = off; off += (long long)c->klat[l].Ms * c->klat[l].Mt; }
     c->theta_len = off;
 
     const long long chunk = c->chunk;
     c->pt_slots = (int)(chunk / 256);
     c->kg_slots = (int)((chunk + KG_ROWS - 1) / KG_ROWS);
     long long acc_len = 4;
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         for (int p = 0; p < 2; p++) { KFactor& F = L.f[p]; F.Mp = (int)rup(F.M, KPAD); F.nb = F.Mp / NB; F.ntc = F.Mp / ZIGP_BN; }
         acc_len += 2LL * L.f[0].Mp * L.f[1].Mp;
@@ -337,7 +342,7 @@ int kron_alloc(zigp_ctx* c, const int Ms[2], const int Mt[2]) {
     c->accum_len = acc_len;
     DA(c->accum, acc_len);
     long long pos = 4;
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         const long long qn = (long long)L.f[0].Mp * L.f[1].Mp;
         L.accQbar = c->accum + pos; pos += qn;
@@ -349,6 +354,7 @@ int kron_alloc(zigp_ctx* c, const int Ms[2], const int Mt[2]) {
         }
     }
     DA(c->pt_partial, (long long)c->pt_slots * 4);
+    DA(c->zero2, 2);
     void* q = nullptr;
     CK(cudaMalloc(&q, 16)); c->allocs.push_back(q); c->info = (int*)q;
     CK(cudaMemset(q, 0, 16));
@@ -356,7 +362,7 @@ int kron_alloc(zigp_ctx* c, const int Ms[2], const int Mt[2]) {
     DA(c->out_dev, c->theta_len + ZIGP_OUT_HEADER);
     CK(cudaMallocHost((void**)&c->theta_pin, (size_t)c->theta_len * sizeof(double)));
     CK(cudaMallocHost((void**)&c->out_pin, (size_t)(c->theta_len + ZIGP_OUT_HEADER) * sizeof(double)));
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
         const long long Msp = L.f[0].Mp, Mtp = L.f[1].Mp, qn = Msp * Mtp;
         // n-splits of the rank updates: the outputs are one or a few 64 x 64 tiles, so the point dimension of a chunk is split until

@@ -113,7 +113,31 @@ struct PointArgs {
     double* gm[2]; double* gv[2];     // scale * d var_exp / d mean, d var
     double* partial;                  // [gridDim.x][4]: sum ll, scale*sum dnoise, sum gv_f, sum gv_g  (+= across chunks)
     int precomputed;                  // 1: mean[]/vr[] already hold the moments (Kronecker path); 0: build them from the row stats
+    int lik;                          // 0: on/off (two latents); 1: Gaussian, latent f only (scripts/svgp.py:201-203); 2: probit Bernoulli,
+                                      //    latent f only (scripts/classifier.py:139-141, 210-217)
 };
+
+// single-latent comparison likelihoods: value and d/d(mean, var), d/d noise
+__device__ __forceinline__ PointOut point_eval_single(int lik, double mf, double vf, double y, double noise) {
+    const double TWO_PI = 6.283185307179586476925;
+    PointOut o{};
+    if (lik == 1) {
+        const double r = y - mf, inv = 1.0 / noise, quad = r * r + vf;
+        o.ll = -0.5 * log(TWO_PI) - 0.5 * log(noise) - 0.5 * quad * inv;
+        o.dmf = r * inv; o.dvf = -0.5 * inv;
+        o.dnoise = -0.5 * inv + 0.5 * quad * inv * inv;
+    } else {
+        const double i1 = 1.0 / (1.0 + vf), s1 = sqrt(i1), z = mf * s1;
+        const double c = 0.5 * (1.0 + erf(z * 0.70710678118654752440)) * (1.0 - 2.0e-3) + 1.0e-3;
+        const bool one = (y == 1.0);                       // tf.equal(y, 1)
+        const double pr = one ? c : 1.0 - c;
+        o.ll = log(pr);
+        const double dz = (one ? 1.0 : -1.0) / pr * (1.0 - 2.0e-3) * exp(-0.5 * z * z) * 0.39894228040143267794;
+        o.dmf = dz * s1; o.dvf = dz * (-0.5 * mf * i1 * s1);
+        o.dnoise = 0.0;
+    }
+    return o;
+}
 
 __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
     __shared__ double sh[32];
@@ -123,6 +147,7 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
         double mean[2], vr[2];
 #pragma unroll
         for (int l = 0; l < 2; l++) {
+            if (l == 1 && p.lik != 0) { mean[l] = 0.0; vr[l] = 0.0; continue; }
             if (p.precomputed) { mean[l] = p.mean[l][r]; vr[l] = p.vr[l][r]; continue; }
             double sa = 0.0, da = 0.0, sra = 0.0;
             for (int t = 0; t < p.ntc[l]; t++) {      // fixed order: deterministic
@@ -135,14 +160,20 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
             p.mean[l][r] = mean[l];
             p.vr[l][r] = vr[l];
         }
-        if (r < p.nvalid) {
+        if (r < p.nvalid && p.lik != 0) {
+            PointOut o = point_eval_single(p.lik, mean[0], vr[0], p.Y[p.n0 + r], p.noise[0]);
+            ll = o.ll; dn = p.scale * o.dnoise;
+            p.gm[0][r] = p.scale * o.dmf; p.gv[0][r] = p.scale * o.dvf;
+            sgf = p.scale * o.dvf;
+        } else if (r < p.nvalid) {
             PointOut o = point_eval(mean[0], vr[0], mean[1], vr[1], p.Y[p.n0 + r], p.noise[0]);
             ll = o.ll; dn = p.scale * o.dnoise;
             p.gm[0][r] = p.scale * o.dmf; p.gv[0][r] = p.scale * o.dvf;
             p.gm[1][r] = p.scale * o.dmg; p.gv[1][r] = p.scale * o.dvg;
             sgf = p.scale * o.dvf; sgg = p.scale * o.dvg;
         } else {
-            p.gm[0][r] = 0.0; p.gv[0][r] = 0.0; p.gm[1][r] = 0.0; p.gv[1][r] = 0.0;
+            p.gm[0][r] = 0.0; p.gv[0][r] = 0.0;
+            if (p.lik == 0) { p.gm[1][r] = 0.0; p.gv[1][r] = 0.0; }
         }
     }
     double t0 = block_sum(ll, sh), t1 = block_sum(dn, sh), t2 = block_sum(sgf, sh), t3 = block_sum(sgg, sh);
@@ -239,6 +270,23 @@ __global__ void reduce_slots_kernel(const double* __restrict__ src, long long st
     double s = 0.0;
     for (int k = 0; k < nslots; k++) s += src[(long long)k * stride + i];
     dst[i] = s;
+}
+
+// predict epilogue of the single-latent comparison models: lik 1 -> rows (fmean, fvar); lik 2 -> rows (p, p - p^2, fmean, fvar)
+// (scripts/svgp.py:123-133, scripts/classifier.py:128-142); the remaining rows of the 9 x n block are zero
+__global__ void predict1_kernel(const double* __restrict__ mf, const double* __restrict__ vf, int nvalid, long long n0, long long ntot, int lik,
+                                double* __restrict__ out9) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nvalid) return;
+    const long long i = n0 + r;
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lik == 1) { v[0] = mf[r]; v[1] = vf[r]; }
+    else {
+        const double z = mf[r] / sqrt(1.0 + vf[r]);
+        const double c = 0.5 * (1.0 + erf(z * 0.70710678118654752440)) * (1.0 - 2.0e-3) + 1.0e-3;
+        v[0] = c; v[1] = c - c * c; v[2] = mf[r]; v[3] = vf[r];
+    }
+    for (int k = 0; k < 9; k++) out9[k * ntot + i] = v[k];
 }
 
 // predict epilogue: the 9 outputs of build_predict (onoffgpf/OnOffSVGP.py:140-152) from the four moments

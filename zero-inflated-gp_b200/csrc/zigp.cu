@@ -113,7 +113,10 @@ struct zigp_ctx {
     // scratch of zigp_debug_gemm (int8 engine)
     int8_t *dbg_pa = nullptr, *dbg_pb = nullptr; double *dbg_sa = nullptr, *dbg_sb = nullptr;
     size_t dbg_cap_a = 0, dbg_cap_b = 0, dbg_cap_r = 0, dbg_cap_c = 0;
-    // Kronecker variant
+    // Kronecker variant; nlat / lik: 2 latents + on/off likelihood (scripts/onoff.py), or the single-latent comparison models
+    // 1 latent + Gaussian likelihood (scripts/svgp.py), 1 latent + probit Bernoulli (scripts/classifier.py)
+    int nlat = 2, lik = 0;
+    double* zero2 = nullptr;
     bool kron = false;
     int Ds = 0, Dt = 0;
     long long off_noise = 0;
@@ -787,7 +790,13 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
 }
 
 int zigp_create_kron(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g, int Mt_g, int Ds, int Dt, double jitter, int64_t chunk_rows) {
+    return zigp_create_kron_ex(out, device, Ms_f, Mt_f, Ms_g, Mt_g, Ds, Dt, jitter, chunk_rows, 0);
+}
+
+int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g, int Mt_g, int Ds, int Dt, double jitter, int64_t chunk_rows, int model) {
     if (!out) return ZIGP_EINVAL;
+    if (model < 0 || model > 2) { g_create_error = "zigp_create_kron_ex: model must be 0 (on/off), 1 (regression) or 2 (classifier)"; return ZIGP_EINVAL; }
+    if (model != 0) { Ms_g = Ms_f; Mt_g = Mt_f; }
     *out = nullptr;
     const int lim = 1 << 14;
     if (Ms_f <= 0 || Mt_f <= 0 || Ms_g <= 0 || Mt_g <= 0 || Ds <= 0 || Dt <= 0 || Ds > ZIGP_MAX_D || Dt > ZIGP_MAX_D || !(jitter >= 0.0) ||
@@ -803,6 +812,7 @@ int zigp_create_kron(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g, i
     }
     zigp_ctx* c = new zigp_ctx();
     c->device = device; c->kron = true; c->Ds = Ds; c->Dt = Dt; c->D = Ds + Dt; c->jitter = jitter;
+    c->nlat = model == 0 ? 2 : 1; c->lik = model;
     auto fail = [&](int code) { g_create_error = c->err; zigp_destroy(c); return code; };
     if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(ZIGP_ECUDA); }
     int cc_major = 0;

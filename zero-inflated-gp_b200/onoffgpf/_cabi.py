@@ -18,6 +18,7 @@ SYMBOLS = {
     "zigp_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
     "zigp_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int]),
     "zigp_create_kron": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64]),
+    "zigp_create_kron_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int]),
     "zigp_destroy": (C.c_int, [C.c_void_p]),
     "zigp_last_error": (C.c_char_p, [C.c_void_p]),
     "zigp_theta_len": (C.c_int64, [C.c_void_p]),
@@ -81,13 +82,13 @@ def check(ctx, rc):
 class Context:
     """Owns one zigp_ctx (one GPU)."""
 
-    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0, kron=None, whiten=False, q_full=False):
+    def __init__(self, device: int, Mf: int, Mg: int, D: int, jitter: float, chunk_rows: int = 0, kron=None, whiten=False, q_full=False, kron_model=0):
         """dense context, or with kron=(Ms_f, Mt_f, Ms_g, Mt_g, Ds, Dt) the Kronecker variant (zigp_create_kron)"""
         self._h = C.c_void_p()
         if kron is None:
             rc = lib().zigp_create_ex(C.byref(self._h), int(device), int(Mf), int(Mg), int(D), float(jitter), int(chunk_rows), int(bool(whiten)), int(bool(q_full)))
         else:
-            rc = lib().zigp_create_kron(C.byref(self._h), int(device), *[int(v) for v in kron], float(jitter), int(chunk_rows))
+            rc = lib().zigp_create_kron_ex(C.byref(self._h), int(device), *[int(v) for v in kron], float(jitter), int(chunk_rows), int(kron_model))
         if rc != 0:
             msg = lib().zigp_last_error(None)
             raise ZigpError("%s (code %d)" % (msg.decode() if msg else "zigp_create failed", rc))
@@ -96,7 +97,10 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            lib().zigp_destroy(self._h)
+            try:
+                lib().zigp_destroy(self._h)
+            except Exception:       # interpreter shutdown: the module globals may already be gone
+                pass
             self._h = C.c_void_p()
 
     __del__ = close

@@ -2,5 +2,6 @@
 from onofftf/main.py (``KernSE``, ``GaussKLkron``, ``DataSet``) -- same parameter names as that script -- evaluated by the
 libzigp Kronecker context (csrc/kron.cuh, csrc/kron_host.cuh)."""
 from .model import DataSet, OnOffKron
+from .baselines import KronClassifier, KronSVGP
 
-__all__ = ["OnOffKron", "DataSet"]
+__all__ = ["OnOffKron", "DataSet", "KronSVGP", "KronClassifier"]
