@@ -370,7 +370,8 @@ def roofline_head(int8, kron, achieved, dgemm_tf, M, m):
         peak = 2.0 * (bf16 if bf16 else 1400.0)
         nsl, sbits, prods = m._ctx.int8_config()
         return {"bound": "tensor", "kernel": "ozaki_gemm_kernel_v2<2> (tcgen05.mma kind::i8, 128x64 tiles, %d x %d-bit slices = %d int8 slice products per fp64 product, TMA multicast in 2-CTA clusters, persistent)" % (nsl, sbits, prods),
-                "achieved": achieved * prods, "peak": peak, "unit": "TOP/s", "frac": achieved * prods / peak, "traffic": None, "slice_products": prods,
+                "achieved": achieved * prods, "peak": peak, "unit": "TOP/s", "frac": achieved * prods / peak,
+                "traffic": traffic_per_launch(M, ctx_chunk_rows(m), "int8") if prods == 28 else None, "slice_products": prods,
                 "peak_source": src, "fp64_equivalent_tflops": achieved, "dgemm_tflops_measured": dgemm_tf,
                 "fp64_equivalent_over_dgemm": achieved / dgemm_tf if dgemm_tf else None}
     return {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": dgemm_tf,
@@ -382,11 +383,11 @@ def ctx_chunk_rows(m):
     return m._ctx.debug_buffer("K", 0)[1]
 
 
-def traffic_per_launch(M, chunk_rows):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tn_f64 launch from the committed `ncu --set full` capture
+def traffic_per_launch(M, chunk_rows, engine="dmma"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/ncu_traffic.json; taken at M=1024, 65536 rows per launch) -- null for any other shape"""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[engine]
         if (M, chunk_rows) == (t["M"], t["rows_per_launch"]):
             return t["dram_bytes_per_launch"]
     except Exception:
