@@ -25,6 +25,7 @@
 #pragma once
 #include "tc05.cuh"
 #include "gemm_f64.cuh"
+#include "../../include/zigp.h"
 #include <algorithm>
 
 namespace zigp {
@@ -114,6 +115,57 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
             const uint32_t pk = (uint32_t)(d[0][p] & 0xff) | ((uint32_t)(d[1][p] & 0xff) << 8) | ((uint32_t)(d[2][p] & 0xff) << 16) | ((uint32_t)(d[3][p] & 0xff) << 24);
             *reinterpret_cast<uint32_t*>(out + (long long)p * plane_stride + k) = pk;
         }
+    }
+}
+
+// Kmn tile construction fused with the slicing of its rows (int8 engine): K[n, m] = var exp(-1/2 |(x_n - z_m) / ell|^2) is written as
+// fp64 (the gradient kernel needs it) AND as NS digit planes with ONE power-of-two scale for all rows, 2^e > 4 var: K <= var, so
+// |K| 2^-e < 1/4 holds without a pass over the row.  A row whose largest entry is far below var keeps fewer significant bits, but
+// the absolute error stays 2^(-8 NS) 4 var -- what the downstream sums (|A|^2 against var, A.alpha_w) are measured against.
+// Thread = 4 consecutive columns of one row per step: 32-byte fp64 stores and 4-byte plane stores, both fully coalesced.
+template <int NS, int DT>
+__global__ void __launch_bounds__(128) kgen_sliced_kernel(const double* __restrict__ X, const double* __restrict__ Z, const double* __restrict__ ell,
+                                                           const double* __restrict__ var, long long n0, int nvalid, int rows, int M, int D, int Mp,
+                                                           double* __restrict__ K, int8_t* __restrict__ planes, long long plane_stride,
+                                                           double* __restrict__ scale) {
+    const int m0 = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
+    const int rsub = threadIdx.x >> 5;
+    double z[4][DT], il[DT];
+#pragma unroll
+    for (int d = 0; d < DT; d++) {
+        il[d] = (d < D) ? 1.0 / ell[d] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) z[j][d] = (d < D && m0 + j < M) ? Z[(long long)(m0 + j) * D + d] : 0.0;
+    }
+    const double v = var[0];
+    const int e = ilogb(v) + EOFF;
+    const double inv = scalbn(1.0, -e), sc = scalbn(1.0, e);
+    for (int rr = 0; rr < 16; rr++) {
+        const int r = blockIdx.y * 64 + rr * 4 + rsub;
+        if (r >= rows) break;
+        double k[4] = {0.0, 0.0, 0.0, 0.0};
+        if (r < nvalid) {
+            double x[DT];
+#pragma unroll
+            for (int d = 0; d < DT; d++) x[d] = (d < D) ? X[(n0 + r) * D + d] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double r2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < DT; d++) { const double t = (x[d] - z[j][d]) * il[d]; r2 = fma(t, t, r2); }
+                k[j] = (m0 + j < M) ? v * exp(-0.5 * r2) : 0.0;
+            }
+        }
+        *reinterpret_cast<double4*>(K + (long long)r * Mp + m0) = make_double4(k[0], k[1], k[2], k[3]);
+        int d4[4][NS];
+#pragma unroll
+        for (int j = 0; j < 4; j++) slice_digits<NS>(k[j] * inv, d4[j]);
+#pragma unroll
+        for (int p = 0; p < NS; p++) {
+            const uint32_t pk = (uint32_t)(d4[0][p] & 0xff) | ((uint32_t)(d4[1][p] & 0xff) << 8) | ((uint32_t)(d4[2][p] & 0xff) << 16) | ((uint32_t)(d4[3][p] & 0xff) << 24);
+            *reinterpret_cast<uint32_t*>(planes + (long long)p * plane_stride + (long long)r * Mp + m0) = pk;
+        }
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) scale[r] = sc;
     }
 }
 
@@ -525,6 +577,25 @@ inline cudaError_t launch_slice_rows(int ns, const double* X, long long ld, int 
     if (ns == NS64) slice_rows_kernel<NS64><<<(rows + 7) / 8, 256, 0, st>>>(X, ld, rows, K, nullptr, planes, plane_stride, scale);
     else if (ns == NS32) slice_rows_kernel<NS32><<<(rows + 7) / 8, 256, 0, st>>>(X, ld, rows, K, nullptr, planes, plane_stride, scale);
     else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// fused Kmn construction + row slicing (dense path; X is n x D row-major)
+inline cudaError_t launch_kgen_sliced(int ns, const double* X, const double* Z, const double* ell, const double* var, long long n0, int nvalid, int rows,
+                                      int M, int D, int Mp, double* K, int8_t* planes, long long plane_stride, double* scale, cudaStream_t st) {
+    const dim3 grid(Mp / 128, rows / 64);
+#define ZIGP_KGS(NSV, DTV) kgen_sliced_kernel<NSV, DTV><<<grid, 128, 0, st>>>(X, Z, ell, var, n0, nvalid, rows, M, D, Mp, K, planes, plane_stride, scale)
+#define ZIGP_KGS_D(NSV)                                  \
+    switch (D) {                                         \
+        case 1: ZIGP_KGS(NSV, 1); break;                 \
+        case 2: ZIGP_KGS(NSV, 2); break;                 \
+        case 3: ZIGP_KGS(NSV, 3); break;                 \
+        case 4: ZIGP_KGS(NSV, 4); break;                 \
+        default: ZIGP_KGS(NSV, ZIGP_MAX_D); break;       \
+    }
+    if (ns == NS64) { ZIGP_KGS_D(NS64) } else if (ns == NS32) { ZIGP_KGS_D(NS32) } else return cudaErrorInvalidValue;
+#undef ZIGP_KGS_D
+#undef ZIGP_KGS
     return cudaGetLastError();
 }
 

@@ -364,18 +364,24 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
     Latent& L = c->lat[l];
     const int Mp = L.Mp;
     dim3 gk(Mp / 32, rows / 64);
-    {
-        ProfScope ps(c, PC_KGEN, st);
-        kgen_kernel<<<gk, 128, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, c->D, 0);
-        LAUNCHED();
-    }
     if (c->engine == 1 && rows % oz::OBM == 0) {
-        RUN(oz_slice_in(c, L, L.Kb, rows, Mp, st));
+        {
+            // Kmn tiles and their digit planes in one kernel (fixed row scale 2^e > 4 var: no max pass, no separate slicing launch)
+            ProfScope ps(c, PC_KGEN, st);
+            CK(oz::launch_kgen_sliced(c->oz_ns, X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, L.oz_in,
+                                      (long long)rows * Mp, L.oz_rs, st));
+            c->launches++;
+        }
         RUN(oz_product(c, L, 0, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, st));               // A = K T^T, |A|^2, A.alpha_w
         RUN(oz_slice_in(c, L, L.Ab, rows, Mp, st));
         RUN(oz_product(c, L, 1, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, st));       // |R A|^2 only: RA is never stored
         if (need_bwd) RUN(oz_product(c, L, 2, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, st));   // Y = G A
         return 0;
+    }
+    {
+        ProfScope ps(c, PC_KGEN, st);
+        kgen_kernel<<<gk, 128, 0, st>>>(X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, c->D, 0);
+        LAUNCHED();
     }
     GemmArgs g{};
     g.rows = rows; g.cols = Mp; g.kdim = Mp; g.alpha = 1.0; g.beta = 0.0;
