@@ -35,6 +35,7 @@ constexpr int NS64 = 7;                       // slices per operand, fp64 precis
 constexpr int NS32 = 4;                       // slices per operand, fp32-class precision
 constexpr int SBITS = 8;                      // bits per slice
 constexpr int EOFF = 3;                       // exponent offset: |x| 2^-e < 1/4, so the leading digit fits a signed byte
+constexpr double RMAGIC = 6755399441055744.0;  // 1.5 * 2^52: x + RMAGIC holds round(x) in its low mantissa word for |x| < 2^31
 constexpr double INVB = 1.0 / 256.0;
 constexpr double INVB2 = INVB * INVB;         // product scale 2^(-2 SBITS)
 constexpr int MAX_ACC_K = 16384;              // longest contraction accumulated in one int32 pass: 7 * 2^14 * K < 2^31
@@ -59,28 +60,36 @@ struct Cfg {
 };
 
 // ---- slicing ------------------------------------------------------------------------------------------------------------
-// 8 NS fractional bits of t (|t| < 1/4) as NS balanced base-256 digits, most significant first.  NS = 7: two double -> int32
-// roundings (28 bits each) and integer digit extraction (the per-slice F2I / I2F chain of the obvious loop is fp64-conversion
-// bound); NS = 4: one rounding to 32 bits.
+// 8 NS fractional bits of t (|t| < 1/4) as NS balanced base-256 digits, most significant first, returned as their two's-complement
+// BYTES (0..255).  The balanced digit of an integer V is its sign-extended low byte and the remaining quotient is (V + 128) >> 8,
+// so a digit costs an add and a shift.  NS = 7: round(t 2^56) does not fit the 53-bit significand; it is formed as two exact
+// 28-bit roundings h1 2^28 + h2 and regrouped into 32-bit words (hi 2^24 + lo), so the whole extraction is 32-bit integer work
+// and the roundings are additions of 1.5 2^52 whose low mantissa word is read back (F2I / I2F on doubles run at a fraction of the
+// DADD rate and made the slicing kernels conversion-bound).  NS <= 4: one rounding to 8 NS <= 32 bits.
 template <int NS>
 __device__ __forceinline__ void slice_digits(double t, int (&d)[NS]) {
-    long long V;
-    if (NS * SBITS > 52) {
+    static_assert(NS == 7 || NS <= 4, "slice_digits: 7 or <= 4 slices");
+    if (NS == 7) {
         const double v1 = t * 268435456.0;                 // 2^28, exact
-        const int h1 = __double2int_rn(v1);
-        const double v2 = (v1 - (double)h1) * 268435456.0; // exact remainder, |.| <= 2^27
-        const int h2 = __double2int_rn(v2);
-        V = ((long long)h1 << 28) + (long long)h2;         // round(t 2^56)
-    } else {
-        V = __double2ll_rn(t * (double)(1LL << (NS * SBITS)));
-    }
-    constexpr long long HALF = 1LL << (SBITS - 1), MASK = (1LL << SBITS) - 1;
+        const double s1 = v1 + RMAGIC;                     // round-to-nearest-even to an integer: |v1| < 2^31, ulp(1.5 2^52) = 1
+        const int h1 = __double2loint(s1);                 // |h1| <= 2^26
+        const double v2 = (v1 - (s1 - RMAGIC)) * 268435456.0;   // exact remainder, |.| <= 2^27
+        const int h2 = __double2loint(v2 + RMAGIC);
+        int lo = h2 & 0xFFFFFF;                            // round(t 2^56) = hi 2^24 + lo
+        int hi = (h1 << 4) + (h2 >> 24);
+        d[NS - 1] = lo & 255; lo = (lo + 128) >> 8;
+        d[NS - 2] = lo & 255; lo = (lo + 128) >> 8;
+        d[NS - 3] = lo & 255; lo = (lo + 128) >> 8;        // carry into the upper word
+        hi += lo;
 #pragma unroll
-    for (int i = NS - 1; i >= 1; i--) {
-        const long long lo = ((V + HALF) & MASK) - HALF;
-        d[i] = (int)lo; V = (V - lo) >> SBITS;
+        for (int i = NS - 4; i >= 1; i--) { d[i] = hi & 255; hi = (hi + 128) >> 8; }
+        d[0] = hi & 255;
+    } else {
+        int w = __double2loint(t * (double)(1LL << (NS * SBITS)) + RMAGIC);     // |w| <= 2^(8 NS - 2)
+#pragma unroll
+        for (int i = NS - 1; i >= 1; i--) { d[i] = w & 255; w = (w + 128) >> 8; }
+        d[0] = w & 255;
     }
-    d[0] = (int)V;
 }
 
 // planes[p][r][k] = X_p of row r (k contiguous, plane stride in bytes), scale[r] = 2^e.  One warp per row; K % 128 == 0.
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(128) kgen_sliced_kernel(const double* __restri
                 k[j] = (m0 + j < M) ? v * exp(-0.5 * r2) : 0.0;
             }
         }
-        *reinterpret_cast<double4*>(K + (long long)r * Mp + m0) = make_double4(k[0], k[1], k[2], k[3]);
+        tc05::st_global_f64x4(K + (long long)r * Mp + m0, k[0], k[1], k[2], k[3]);
         int d4[4][NS];
 #pragma unroll
         for (int j = 0; j < 4; j++) slice_digits<NS>(k[j] * inv, d4[j]);
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restric
     __syncthreads();
     // thread -> (column cc, 16 consecutive n): 32 columns x 4 groups of 16
     const int cc = threadIdx.x >> 2, grp = threadIdx.x & 3;
-    for (int pass = 0; pass < (rowweight ? 2 : 1); pass++) {
+    for (int pass = planes ? 0 : 1; pass < (rowweight ? 2 : 1); pass++) {     // planes == null: only the weighted operand (the plain one came from a fused epilogue)
         const double mx = __longlong_as_double((long long)(pass ? colmax2 : colmax)[c0 + cc]);
         int e = 0;
         if (mx > 0.0) e = ilogb(mx) + EOFF;
@@ -242,6 +251,12 @@ struct OzArgs {
     double* stat_sq; double* stat_dot; const double* dotvec; double* OutSq;   // same meaning as GemmArgs
     int lower_only;                             // rank-update use: skip tiles that lie entirely above the diagonal
     int nsplit; long long split_stride;         // TRI_FULL only: the k range is dealt to gridDim.y splits, split s writes Out + s * split_stride
+    // Fused re-slicing of the result for the next contraction (nsplit == 1): digit planes of Out under ONE power-of-two scale
+    // 2^e > 4 sqrt(*sl_bound2), valid when every |Out| <= sqrt(*sl_bound2) (the whitened cross-covariance A: |A_n|^2 <= var).
+    const double* sl_bound2;
+    int8_t* sl_rows; double* sl_rscale;         // planes[p][r][c] (row operand of the next product), scale per row    (may be null)
+    int8_t* sl_cols; double* sl_cscale;         // planes[p][c][r] (transposed: operand of the rank update), scale per column (may be null)
+    long long sl_stride;                        // plane stride in bytes (rows * cols)
 };
 
 __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
@@ -456,24 +471,67 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             double* Out = g.Out + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0);
             const double* Zin = g.Zin ? g.Zin + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0) : nullptr;
             double ssq = 0.0, sdt = 0.0;
+            const bool reslice = g.sl_bound2 != nullptr;
+            double sl_inv = 0.0;
+            if (reslice) {
+                const int e = ilogb(sqrt(g.sl_bound2[0])) + EOFF;
+                sl_inv = scalbn(1.0, -e);
+                const double sc = scalbn(1.0, e);
+                if (g.sl_rscale && col0 == 0 && h == 0) g.sl_rscale[r] = sc;
+                if (g.sl_cscale && row0 == 0 && q == 0) g.sl_cscale[col0 + h * 32 + lane] = sc;
+            }
+            uint32_t wr[2][NS][4];
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
                 const int c = col0 + h * 32 + ch * 16;
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    double v0 = g.alpha * (acc[ch][j] * rs * g.cscale[c + j]);
-                    double v1 = g.alpha * (acc[ch][j + 1] * rs * g.cscale[c + j + 1]);
+                for (int p = 0; p < NS; p++) { wr[ch][p][0] = 0; wr[ch][p][1] = 0; wr[ch][p][2] = 0; wr[ch][p][3] = 0; }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    double v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) v[i] = g.alpha * (acc[ch][j + i] * rs * g.cscale[c + j + i]);
                     if (g.beta != 0.0) {
-                        const double2 z = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j);
-                        v0 += g.beta * z.x; v1 += g.beta * z.y;
+                        const double2 z0 = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j);
+                        const double2 z1 = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j + 2);
+                        v[0] += g.beta * z0.x; v[1] += g.beta * z0.y; v[2] += g.beta * z1.x; v[3] += g.beta * z1.y;
                     }
-                    if (g.Out) *reinterpret_cast<double2*>(Out + (long long)r * g.ldo + c + j) = make_double2(v0, v1);
-                    if (g.OutSq) *reinterpret_cast<double2*>(g.OutSq + (long long)r * g.ldo + c + j) = make_double2(v0 * v0, v1 * v1);
+                    // 32-byte stores (STG.256): a thread owns 32 consecutive columns of its row, so every store fills whole sectors
+                    if (g.Out) tc05::st_global_f64x4(Out + (long long)r * g.ldo + c + j, v[0], v[1], v[2], v[3]);
+                    if (g.OutSq) tc05::st_global_f64x4(g.OutSq + (long long)r * g.ldo + c + j, v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3]);
                     if (g.stat_sq) {
-                        ssq = fma(v0, v0, ssq); ssq = fma(v1, v1, ssq);
-                        if (g.dotvec) { sdt = fma(v0, g.dotvec[c + j], sdt); sdt = fma(v1, g.dotvec[c + j + 1], sdt); }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) ssq = fma(v[i], v[i], ssq);
+                        if (g.dotvec) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) sdt = fma(v[i], g.dotvec[c + j + i], sdt);
+                        }
+                    }
+                    if (reslice) {
+                        int d[4][NS];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) slice_digits<NS>(v[i] * sl_inv, d[i]);
+#pragma unroll
+                        for (int p = 0; p < NS; p++)
+                            wr[ch][p][j >> 2] = (uint32_t)(d[0][p] & 0xff) | ((uint32_t)(d[1][p] & 0xff) << 8) | ((uint32_t)(d[2][p] & 0xff) << 16) | ((uint32_t)(d[3][p] & 0xff) << 24);
+                        if (g.sl_cols) {
+                            // transposed planes: the 32 lanes of a warp are 32 consecutive rows -> one full 32-byte sector per store
+                            int8_t* oc = g.sl_cols + (long long)(c + j) * g.rows + r;
+#pragma unroll
+                            for (int p = 0; p < NS; p++) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) oc[(long long)p * g.sl_stride + (long long)i * g.rows] = (int8_t)d[i][p];
+                            }
+                        }
                     }
                 }
+            }
+            if (reslice && g.sl_rows) {
+                int8_t* orow = g.sl_rows + (long long)r * g.cols + col0 + h * 32;
+#pragma unroll
+                for (int p = 0; p < NS; p++)
+                    tc05::st_global_b32x8(orow + (long long)p * g.sl_stride, make_uint4(wr[0][p][0], wr[0][p][1], wr[0][p][2], wr[0][p][3]),
+                                          make_uint4(wr[1][p][0], wr[1][p][1], wr[1][p][2], wr[1][p][3]));
             }
             if (g.stat_sq) {
                 // combine the two column halves of a row (fixed order -> deterministic); named barrier of the 256 epilogue threads

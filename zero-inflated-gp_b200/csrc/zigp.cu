@@ -45,8 +45,8 @@ struct Latent {
     double *Lq = nullptr, *Lqt = nullptr, *PE = nullptr, *Sab = nullptr, *Tbar = nullptr, *RbT = nullptr, *RbTt = nullptr, *Bm = nullptr, *Phi = nullptr,
            *Kinv = nullptr, *gLq = nullptr;
     // per-latent slice workspaces (the two latents run on two streams): row operand of the products, A / gv*A transposed
-    int8_t *oz_in = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;
-    double *oz_rs = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
+    int8_t *oz_in = nullptr, *oz_inA = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;
+    double *oz_rs = nullptr, *oz_rsA = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
     unsigned long long* oz_colmax = nullptr;
     int nsplit_oz = 4;
 };
@@ -107,6 +107,7 @@ struct zigp_ctx {
     // contraction engine: 0 = DMMA (gemm_f64.cuh), 1 = fp64 on the int8 tensor cores (ozaki.cuh); dense path only
     int engine = 0;
     bool oz_ready = false;
+    int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
     int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
     // second stream for latent g (the int8 contractions of one latent overlap the fp64 / memory-bound kernels of the other)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -339,22 +340,29 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
     return 0;
 }
 
-// int8 engine: one contraction of the chunk's sliced row operand (c->oz_in / c->oz_rs) with pre-sliced factor `wi` of the latent
-int oz_product(zigp_ctx* c, Latent& L, int wi, int rows, int tri, double* Out, double* stat_sq, double* stat_dot, const double* dotvec, cudaStream_t st) {
+// int8 engine: one contraction of a sliced row operand of the chunk (K: oz_in / oz_rs, A: oz_inA / oz_rsA) with pre-sliced factor
+// `wi` of the latent.  reslice = 1: the epilogue also emits the digit planes of the result (A) for the next products, 2: and its
+// transposed planes for the rank update (fixed scale from |A_nm| <= sqrt(var)).
+int oz_product(zigp_ctx* c, Latent& L, int wi, bool from_A, int rows, int tri, double* Out, double* stat_sq, double* stat_dot, const double* dotvec,
+               int reslice, const double* bound2, cudaStream_t st) {
     const int Mp = L.Mp;
-    oz::OzOperand A{L.oz_in, Mp, rows, (long long)rows * Mp, L.oz_rs};
+    oz::OzOperand A{from_A ? L.oz_inA : L.oz_in, Mp, rows, (long long)rows * Mp, from_A ? L.oz_rsA : L.oz_rs};
     oz::OzOperand B{L.ozW[wi], Mp, Mp, (long long)Mp * Mp, L.ozWs[wi]};
     oz::OzArgs a{};
     a.Out = Out; a.ldo = Mp; a.alpha = 1.0; a.beta = 0.0; a.rows = rows; a.cols = Mp; a.kdim = Mp; a.tri = tri;
     a.stat_sq = stat_sq; a.stat_dot = stat_dot; a.dotvec = dotvec; a.nsplit = 1;
+    if (reslice) {
+        a.sl_bound2 = bound2; a.sl_rows = L.oz_inA; a.sl_rscale = L.oz_rsA; a.sl_stride = (long long)rows * Mp;
+        if (reslice > 1) { a.sl_cols = L.oz_colA; a.sl_cscale = L.oz_csA; }
+    }
     ProfScope ps(c, PC_GEMM, st);
     CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, a, st));
     c->launches++;
     return 0;
 }
-int oz_slice_in(zigp_ctx* c, Latent& L, const double* X, int rows, int Mp, cudaStream_t st) {
+int oz_slice_A(zigp_ctx* c, Latent& L, int rows, int Mp, cudaStream_t st) {
     ProfScope ps(c, PC_SLICE, st);
-    CK(oz::launch_slice_rows(c->oz_ns, X, Mp, rows, Mp, L.oz_in, (long long)rows * Mp, L.oz_rs, st));
+    CK(oz::launch_slice_rows(c->oz_ns, L.Ab, Mp, rows, Mp, L.oz_inA, (long long)rows * Mp, L.oz_rsA, st));
     c->launches++;
     return 0;
 }
@@ -372,10 +380,12 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
                                       (long long)rows * Mp, L.oz_rs, st));
             c->launches++;
         }
-        RUN(oz_product(c, L, 0, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, st));               // A = K T^T, |A|^2, A.alpha_w
-        RUN(oz_slice_in(c, L, L.Ab, rows, Mp, st));
-        RUN(oz_product(c, L, 1, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, st));       // |R A|^2 only: RA is never stored
-        if (need_bwd) RUN(oz_product(c, L, 2, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, st));   // Y = G A
+        // A = K T^T, |A|^2, A.alpha_w; the epilogue re-slices A for the next products (and, oz_fuse == 2, for the rank update)
+        const int fuse = c->oz_fuse >= 2 && !need_bwd ? 1 : c->oz_fuse;
+        RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
+        if (!fuse) RUN(oz_slice_A(c, L, rows, Mp, st));
+        RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
+        if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));   // Y = G A
         return 0;
     }
     {
@@ -441,8 +451,9 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
         // E += Aw^T A on the int8 engine: the operands are the columns of Aw and A (k index = point), sliced transposed
         {
             ProfScope ps(c, PC_SLICE, st);
-            CK(oz::launch_slice_cols_pair(c->oz_ns, L.Ab, L.Mp, rows, L.Mp, L.gv, L.oz_colmax, L.oz_colmax + L.Mp, L.oz_colA, L.oz_colAw,
-                                          (long long)L.Mp * rows, L.oz_csA, L.oz_csAw, st));
+            // oz_fuse == 2: the planes of A itself were written by the epilogue of the A product; only gv * A is sliced here
+            CK(oz::launch_slice_cols_pair(c->oz_ns, L.Ab, L.Mp, rows, L.Mp, L.gv, L.oz_colmax, L.oz_colmax + L.Mp, c->oz_fuse >= 2 ? nullptr : L.oz_colA,
+                                          L.oz_colAw, (long long)L.Mp * rows, L.oz_csA, L.oz_csAw, st));
             c->launches++;
         }
         oz::OzOperand A{L.oz_colAw, rows, L.Mp, (long long)L.Mp * rows, L.oz_csAw};
@@ -789,6 +800,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
         return fail(ZIGP_ECUDA);
     }
     // default engine: fp64 on the int8 tensor cores; ZIGP_ENGINE=dmma (or zigp_set_engine(ctx, 0)) selects the DMMA engine
+    if (const char* fz = getenv("ZIGP_OZ_FUSE")) c->oz_fuse = atoi(fz);
     const char* env = getenv("ZIGP_ENGINE");
     if (!(env && std::string(env) == "dmma") && zigp_set_engine(c, 1) != ZIGP_OK) c->engine = 0;
     *out = c;
@@ -1046,10 +1058,11 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
         for (int l = 0; l < 2; l++) {
             Latent& L = c->lat[l];
             RUN(balloc((void**)&L.oz_in, (size_t)oz::NS64 * chunk * L.Mp));
+            RUN(balloc((void**)&L.oz_inA, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colA, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colAw, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colmax, (size_t)2 * L.Mp * sizeof(unsigned long long)));
-            DA(L.oz_rs, chunk); DA(L.oz_csA, L.Mp); DA(L.oz_csAw, L.Mp);
+            DA(L.oz_rs, chunk); DA(L.oz_rsA, chunk); DA(L.oz_csA, L.Mp); DA(L.oz_csAw, L.Mp);
             for (int i = 0; i < 3; i++) {
                 RUN(balloc((void**)&L.ozW[i], (size_t)oz::NS64 * L.Mp * L.Mp));
                 DA(L.ozWs[i], L.Mp);
