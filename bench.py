@@ -131,12 +131,40 @@ def cpu_kron_rate(N_sample, Ms, Mt, steps, warmup):
     return N_sample / dt, dt, torch.get_num_threads()
 
 
+DATA_BLOCK = 1 << 20
+
+
+def shard_data(synth, lo, hi, D):
+    """rows [lo, hi) of the synthetic data set: block b = synth.make_data(2^20, D, seed=1000 + b)"""
+    Xs, Ys = [], []
+    for b in range(lo // DATA_BLOCK, (hi - 1) // DATA_BLOCK + 1):
+        Xb, Yb = synth.make_data(DATA_BLOCK, D, seed=1000 + b)
+        s0, s1 = max(lo, b * DATA_BLOCK) - b * DATA_BLOCK, min(hi, (b + 1) * DATA_BLOCK) - b * DATA_BLOCK
+        Xs.append(Xb[s0:s1]); Ys.append(Yb[s0:s1])
+    return np.concatenate(Xs), np.concatenate(Ys)
+
+
+def host_threads():
+    """threads for the CPU legs: the physical cores of the box (torchrun exports OMP_NUM_THREADS=1, which would cripple the reference arm)"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        n = 0
+    try:
+        n = min(n, len(os.sched_getaffinity(0))) if n else len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = n or (os.cpu_count() or 1)
+    return max(n, torch.get_num_threads(), 1)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if a.workload == "kron":
         ns = min(a.cpu_sample, 1024)
+        torch.set_num_threads(host_threads())
         rate, dt, threads = cpu_kron_rate(ns, a.ms, a.mt, max(1, a.steps), max(1, a.warmup))
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -145,7 +173,7 @@ def run_reference(a):
                                            "sample": "N_b=%d points per step (dense kron(K0^-1,K1^-1) @ Kmn as in scripts/onoff.py:207)" % ns},
                           "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
-    rate, dt, threads = cpu_oracle_rate(a.cpu_sample, a.m, a.d, max(1, a.steps), max(1, a.warmup))
+    rate, dt, threads = cpu_oracle_rate(a.cpu_sample, a.m, a.d, max(1, a.steps), max(1, a.warmup), threads=host_threads())
     sample = "N_b=%d points of the same synthetic workload per step (Kmn is materialised, so the full N does not fit); float64" % a.cpu_sample
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -192,11 +220,12 @@ def run_ours(a):
     lo, hi = shard_bounds(N, rank, world)
     n_loc = hi - lo
 
-    # synthetic data: generated per shard with a shard-specific seed (no rank needs the whole 2^24 x 3 array)
+    # synthetic data: generated in fixed blocks of 2^20 points with block-specific seeds, so no rank needs the whole array and the
+    # data set (hence the ELBO printed in `config`) is the same whatever the number of ranks
     kron = a.workload == "kron"
     if kron:
         D = 3
-    X, Y = synth.make_data(n_loc, D, seed=1000 + rank)
+    X, Y = shard_data(synth, lo, hi, D)
     Xh = torch.as_tensor(X).pin_memory(); Yh = torch.as_tensor(Y.reshape(-1)).pin_memory()
     if kron:
         from onofftf import OnOffKron
@@ -312,7 +341,9 @@ def run_ours(a):
 
     if rank == 0:
         cpu = None
-        if not a.no_cpu_baseline and kron:
+        if world > 1:
+            pass                 # the CPU baseline leg runs at N = 1 only
+        elif not a.no_cpu_baseline and kron:
             ns = min(a.cpu_sample, 1024)
             rate, dt, threads = cpu_kron_rate(ns, a.ms, a.mt, steps=3, warmup=1)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
