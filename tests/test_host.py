@@ -88,3 +88,30 @@ def test_synth_grid_and_zero_inflation():
     X, Y = synth.make_data(5000, 3, 0)
     frac0 = float((Y == 0.0).mean())
     assert 0.2 < frac0 < 0.8 and X.min() >= 0 and X.max() <= 1
+
+
+def test_kron_trainer_recipes():
+    """cross-validation splits, inducing initialisation, clipped error summaries and the two-stage combiners (onofftf/utils.py)"""
+    from onofftf import utils
+    rng = np.random.default_rng(0)
+    X = np.column_stack([rng.random(200) * 10, rng.random(200) * 10, rng.random(200) * 5000.0])
+    Y = np.where(rng.random(200) > 0.7, rng.random(200), 0.0).reshape(-1, 1)
+    folds = list(utils.cv_splits(X, Y))
+    assert [f for f, _ in folds] == [1, 2, 3, 4, 5]
+    seen = np.concatenate([d["Xtest"][:, 0] for _, d in folds])
+    assert sorted(seen) == sorted(X[:, 0])                         # every row is a test row exactly once
+    for _, d in folds:
+        assert d["Xtrain"].shape[0] + d["Xtest"].shape[0] == 200 and d["Ytrain"].shape == (d["Xtrain"].shape[0], 1)
+        assert d["Xtrain"][:, 2].max() <= 5.0                      # time column / 1000
+    again = list(utils.cv_splits(X, Y))
+    assert all(np.array_equal(a[1]["Xtest"], b[1]["Xtest"]) for a, b in zip(folds, again))      # fixed random_state
+    Zs, Zt = utils.init_inducing(folds[0][1]["Xtrain"], (4, 7), seed=1)
+    assert Zs.shape[1] == 2 and Zs.shape[0] <= 4 and Zt.shape == (7, 1)
+    tcol = folds[0][1]["Xtrain"][:, 2]
+    assert Zt[0, 0] == tcol.min() and Zt[-1, 0] == tcol.max() and np.allclose(np.diff(Zt[:, 0]), np.diff(Zt[:, 0])[0])
+    pred, act = np.array([-1.0, 2.0, 0.5]), np.array([0.0, 1.0, 0.5])
+    assert utils.rmse(pred, act) == pytest.approx(np.sqrt(1.0 / 3.0)) and utils.mae(pred, act) == pytest.approx(1.0 / 3.0)
+    p, m = np.array([[0.9], [0.2], [0.6]]), np.array([[2.0], [3.0], [-1.0]])
+    soft, hard = utils.zero_inflated_combine(p, m)
+    assert np.allclose(soft, [[1.8], [0.6], [-0.6]]) and np.allclose(hard, [[2.0], [0.0], [-1.0]])
+    assert list(utils.hurdle_select(p)) == [0, 2]

@@ -3,5 +3,6 @@ from onofftf/main.py (``KernSE``, ``GaussKLkron``, ``DataSet``) -- same paramete
 libzigp Kronecker context (csrc/kron.cuh, csrc/kron_host.cuh)."""
 from .model import DataSet, OnOffKron
 from .baselines import KronClassifier, KronSVGP
+from . import utils
 
-__all__ = ["OnOffKron", "DataSet", "KronSVGP", "KronClassifier"]
+__all__ = ["OnOffKron", "DataSet", "KronSVGP", "KronClassifier", "utils"]
