@@ -219,11 +219,11 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
     double z[DT], s1[DT], q[DT];
 #pragma unroll
     for (int d = 0; d < DT; d++) { z[d] = (d < p.D && m < p.M) ? p.Z[m * p.D + d] : 0.0; s1[d] = 0.0; q[d] = 0.0; }
-    const double bm = p.beta[m];
     double s0 = 0.0, am = 0.0, mxa = 0.0, mxw = 0.0;
+    const double* Ap = p.A + (long long)r0 * p.ld + m;
+    const double bm = p.beta[m];
     const double* Kp = p.K + (long long)r0 * p.ld + m;
     const double* Yp = p.Y + (long long)r0 * p.ld + m;
-    const double* Ap = p.A + (long long)r0 * p.ld + m;
     double* Awp = p.Aw + (long long)r0 * p.ld + m;
 #pragma unroll 8
     for (int r = 0; r < nr; r++) {

@@ -43,7 +43,7 @@ constexpr int MAX_ACC_K = 16384;              // longest contraction accumulated
 #define ZIGP_OZ_CL 2
 #endif
 #ifndef ZIGP_OZ_EXP
-#define ZIGP_OZ_EXP 0          // 1 / 2: bottleneck experiments (wrong results), see profiles/int8_bottleneck_r01.txt
+#define ZIGP_OZ_EXP 0          // 9: record the phase timestamps of CTA 0 (tests/oz_trace.py, profiles/int8_gemm_phases_r01.txt)
 #endif
 constexpr int OBM = 128, OBN = 64;            // tile rows, tile columns
 constexpr int UK = 32;                        // k depth of one tcgen05.mma kind::i8 (bytes == int8 elements)
@@ -265,6 +265,14 @@ __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
     return n;
 }
 
+#if ZIGP_OZ_EXP == 9
+// experiment: phase timestamps (SM clock) of CTA 0: per computed tile [mma_start, mma_issued, epi_wait, epi_full, drain_end, write_end, 0, 0]
+__device__ long long oz_trace[8 * 256];
+#define OZ_TRACE(slot, idx) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 256) oz_trace[(slot) * 8 + (idx)] = clock64(); } while (0)
+#else
+#define OZ_TRACE(slot, idx) do { } while (0)
+#endif
+
 template <int NS, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                                                                       const __grid_constant__ CUtensorMap mapB, const OzArgs g) {
@@ -364,10 +372,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     const uint32_t ph = (gi / OSTAGES) & 1u;
                     const bool active = compute && k0 >= kb && k0 < ke;
                     tc05::mbar_wait(&empty[s], ph ^ 1u);
-#if ZIGP_OZ_EXP == 2
-                    tc05::mbar_arrive(&full[s]);            // experiment: no operand traffic at all (MMAs run on stale shared memory)
-                    continue;
-#endif
                     tc05::mbar_arrive_expect_tx(&full[s], A_STAGE + (active ? B_STAGE : 0));
                     uint8_t* dstA = sA + (size_t)s * A_STAGE + (size_t)rank * PL * OBM * OBK;
                     const CUtensorMap* mA = (NS % CL != 0 && rank == CL - 1) ? &mapA2 : &mapA;
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 if (compute) {
                     tc05::mbar_wait(tmem_empty, (ti & 1u) ^ 1u);          // the epilogue has drained the previous tile
                     tc05::fence_after_thread_sync();
+                    OZ_TRACE(ti, 0);
                 }
                 bool first = true;
                 for (int k0 = ckb; k0 < cke; k0 += OBK, gi++) {
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     const bool active = compute && k0 >= kb && k0 < ke;
                     tc05::mbar_wait(&full[s], ph);
                     tc05::fence_after_thread_sync();
-                    if (active && ZIGP_OZ_EXP != 1) {       // experiment 1: operand traffic and barriers only, no MMAs
+                    if (active) {
                         const uint32_t a_base = tc05::smem_u32(sA + (size_t)s * A_STAGE);
                         const uint32_t b_base = tc05::smem_u32(sB + (size_t)s * B_STAGE);
 #pragma unroll
@@ -417,7 +422,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     }
                     if (CL > 1) tc05::mma_commit_mcast(&empty[s], CMASK); else tc05::mma_commit(&empty[s]);
                 }
-                if (compute) { tc05::mma_commit(tmem_full); ti++; }
+                if (compute) { tc05::mma_commit(tmem_full); OZ_TRACE(ti, 1); ti++; }
             }
         }
     } else {
@@ -431,8 +436,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             if (!any || !compute) continue;
             const int r = row0 + rl;
             const int tc = col0 / OBN;
+            // this lane's column scale, dot-vector entry and row scale, requested while the MMAs of the tile are still running; the epilogue
+            // broadcasts them by shuffle (a global load issued after the accumulators arrive waits ~2000 cycles behind the MMA's operand traffic)
+            const double cs_l = __ldg(g.cscale + col0 + h * 32 + lane);
+            const double dv_l = g.dotvec ? __ldg(g.dotvec + col0 + h * 32 + lane) : 0.0;
+            const double rs = g.rscale[r] * INVB2;
+            if (warp == 2 && lane == 0) OZ_TRACE(ti, 2);
             tc05::mbar_wait(tmem_full, ti & 1u);
             tc05::fence_after_thread_sync();
+            if (warp == 2 && lane == 0) OZ_TRACE(ti, 3);
             double acc[2][16];
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
@@ -465,9 +477,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             tc05::fence_before_thread_sync();
             __syncwarp();
             if (lane == 0) tc05::mbar_arrive(tmem_empty);
+            if (warp == 2 && lane == 0) OZ_TRACE(ti, 4);
             ti++;
 
-            const double rs = g.rscale[r] * INVB2;
             double* Out = g.Out + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0);
             const double* Zin = g.Zin ? g.Zin + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0) : nullptr;
             double ssq = 0.0, sdt = 0.0;
@@ -483,6 +495,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             uint32_t wr[2][NS][4];
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc[ch][j] = g.alpha * (acc[ch][j] * rs * __shfl_sync(0xffffffffu, cs_l, ch * 16 + j));
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
                 const int c = col0 + h * 32 + ch * 16;
 #pragma unroll
                 for (int p = 0; p < NS; p++) { wr[ch][p][0] = 0; wr[ch][p][1] = 0; wr[ch][p][2] = 0; wr[ch][p][3] = 0; }
@@ -490,7 +507,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 for (int j = 0; j < 16; j += 4) {
                     double v[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) v[i] = g.alpha * (acc[ch][j + i] * rs * g.cscale[c + j + i]);
+                    for (int i = 0; i < 4; i++) v[i] = acc[ch][j + i];
                     if (g.beta != 0.0) {
                         const double2 z0 = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j);
                         const double2 z1 = *reinterpret_cast<const double2*>(Zin + (long long)r * g.ldz + c + j + 2);
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                         for (int i = 0; i < 4; i++) ssq = fma(v[i], v[i], ssq);
                         if (g.dotvec) {
 #pragma unroll
-                            for (int i = 0; i < 4; i++) sdt = fma(v[i], g.dotvec[c + j + i], sdt);
+                            for (int i = 0; i < 4; i++) sdt = fma(v[i], __shfl_sync(0xffffffffu, dv_l, ch * 16 + j + i), sdt);
                         }
                     }
                     if (reslice) {
@@ -533,6 +550,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     tc05::st_global_b32x8(orow + (long long)p * g.sl_stride, make_uint4(wr[0][p][0], wr[0][p][1], wr[0][p][2], wr[0][p][3]),
                                           make_uint4(wr[1][p][0], wr[1][p][1], wr[1][p][2], wr[1][p][3]));
             }
+            if (warp == 2 && lane == 0) OZ_TRACE(ti - 1, 5);
             if (g.stat_sq) {
                 // combine the two column halves of a row (fixed order -> deterministic); named barrier of the 256 epilogue threads
                 sstat[h][0][rl] = ssq; sstat[h][1][rl] = sdt;

@@ -13,7 +13,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // ---- 256-bit global stores (sm_100: STG.256) -----------------------------------------------------------------------------
 __device__ __forceinline__ void st_global_f64x4(double* p, double a, double b, double c, double d) {
-    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d));   // no memory clobber: callers never read back what they store, and loads must be free to move above
 }
 __device__ __forceinline__ void st_global_b32x8(void* p, uint4 a, uint4 b) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),

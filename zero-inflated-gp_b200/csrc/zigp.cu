@@ -385,7 +385,7 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
         RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
         if (!fuse) RUN(oz_slice_A(c, L, rows, Mp, st));
         RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
-        if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));   // Y = G A
+        if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));
         return 0;
     }
     {
@@ -737,7 +737,6 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     c->chunk = chunk;
     c->pt_slots = (int)(chunk / 256);
     c->kg_slots = (int)((chunk + KG_ROWS - 1) / KG_ROWS);
-
     // packed accumulator: header(4) + per latent [E (Mp^2), vec block (2+2D) Mp]
     long long acc_len = 4;
     for (int l = 0; l < 2; l++) {
@@ -867,6 +866,11 @@ int zigp_destroy(zigp_ctx* c) {
 
 const char* zigp_last_error(const zigp_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 int64_t zigp_theta_len(const zigp_ctx* c) { return c ? c->theta_len : 0; }
+#if ZIGP_OZ_EXP == 9
+int zigp_debug_trace(long long* out_host, int n) {        // experiment builds only: copy the phase timestamps of the last int8 contraction
+    return cudaMemcpyFromSymbol(out_host, oz::oz_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
 int64_t zigp_launch_count(const zigp_ctx* c) { return c ? c->launches : 0; }
 
 int zigp_set_data_dev(zigp_ctx* c, const double* X, const double* Y, int64_t n, double scale) {
