@@ -1,7 +1,10 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-ZIGP_LIB=profiles/microbench/libzigp_exp9.so timeout 200 python tests/oz_trace.py 0 2>/dev/null
-ZIGP_LIB=profiles/microbench/libzigp_exp9.so timeout 200 python tests/oz_trace.py 1 2>/dev/null
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_full_v7.json 2>/dev/null; python -c "
-import json
-d=json.loads(open('gpurun_out/bench_full_v7.json').read().strip().splitlines()[-1])
-print('full: value %.4g e2e %.4g ms %.1f frac %.3f clocks %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],d['roofline']['frac'],d['clocks']))"
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_int8_engine.py -x -q -m gpu 2>&1 | tail -2
+run() {
+env $1 timeout 200 python bench.py --points 1048576 --steps 3 --warmup 3 --no-cpu-baseline --chunk 65536 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+c=d[\"roofline\"][\"class_ms\"]
+print(\"$1 ms/step %.1f elbo %.15e gemm %.1f syrk %.1f slice %.1f kgen %.1f kgrad %.1f clocks %s\"%(d[\"ms_per_step\"],d[\"config\"][\"elbo\"],c[\"gemm_tn\"],c[\"syrk\"],c[\"slice\"],c[\"kgen\"],c[\"kgrad\"],d[\"clocks\"][\"sm_mhz\"]))"
+}
+run "ZIGP_X=kgd128"
+run "ZIGP_ENGINE=dmma"

@@ -104,3 +104,26 @@ def test_rank_update_split_guard_on_a_short_last_chunk():
     a, b = outs["int8"], outs["dmma"]
     assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0])
     assert np.linalg.norm(a[4:] - b[4:]) <= 1e-10 * np.linalg.norm(b[4:])
+
+
+def test_reslicing_modes_agree(monkeypatch):
+    """ZIGP_OZ_FUSE = 0 (A re-sliced by separate kernels, per-row maxima), 1 (digit planes of A from the A product's epilogue, fixed
+    scale from |A_nm| <= sqrt(var); the default) and 2 (also the transposed planes for the rank update): same ELBO to 1e-12 and the same
+    packed gradient to 1e-10 of its norm, on a ragged two-chunk problem whose far-away points exercise rows with tiny |A|"""
+    N, M, D = 70_001, 192, 2
+    X, Y = synth.make_data(N, D, 21)
+    X[:500] += 3.0                                   # points far from every inducing point: K and A rows ~ 1e-200
+    p = synth.make_params(M, M, D, 21)
+    outs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("ZIGP_OZ_FUSE", mode)
+        m = synth.build_model(X, Y, p, engine="int8", chunk_rows=65536)
+        m.build_likelihood()
+        outs[mode] = m._last_out.cpu().numpy()
+        del m
+    ref = outs["0"]
+    for mode in ("1", "2"):
+        a = outs[mode]
+        assert np.all(np.isfinite(a))
+        assert abs(a[0] - ref[0]) <= 1e-12 * abs(ref[0])
+        assert np.linalg.norm(a[2:] - ref[2:]) <= 1e-10 * np.linalg.norm(ref[2:])

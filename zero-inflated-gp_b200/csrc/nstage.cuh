@@ -187,9 +187,10 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
 // Kmn-side kernel gradient sums.  With  kbar[n,m] = gm_n * beta_m - 2 gv_n * Y[n,m]  and  G = kbar * K :
 //   S0[m]   += sum_n G              S1[d][m] += sum_n G (x_nd - z_md)        Q[d][m] += sum_n G (x_nd - z_md)^2
 //   a[m]    += sum_n gm_n A[n,m]                 and writes Aw[n,m] = gv_n A[n,m] for the symmetric rank update
-// Block = 128 columns x KG_ROWS rows; partial sums land in slot [blockIdx.y] (owned by this CTA across chunks).
+// Block = 128 columns x KGD_ROWS rows; partial sums land in slot [blockIdx.y] (owned by this CTA across chunks).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int KG_ROWS = 256;
+constexpr int KG_ROWS = 256;        // Kronecker variant (kron.cuh)
+constexpr int KGD_ROWS = 128;       // dense path: 8 x chunk/128 blocks (4.6 waves at 65536 rows instead of 2.3: the tail wave cost 20 %), 10 KB of shared memory
 struct KgradArgs {
     const double* K; const double* Y; const double* A; long long ld;
     const double* gm; const double* gv; const double* beta;
@@ -202,13 +203,13 @@ struct KgradArgs {
 
 template <int DT>
 __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
-    __shared__ double sx[KG_ROWS][ZIGP_MAX_D];
-    __shared__ double sgm[KG_ROWS], sgv[KG_ROWS];
+    __shared__ double sx[KGD_ROWS][DT];
+    __shared__ double sgm[KGD_ROWS], sgv[KGD_ROWS];
     const int m = blockIdx.x * 128 + threadIdx.x;
-    const int r0 = blockIdx.y * KG_ROWS;
-    const int nr = min(KG_ROWS, p.nvalid - r0);
+    const int r0 = blockIdx.y * KGD_ROWS;
+    const int nr = min(KGD_ROWS, p.nvalid - r0);
     if (nr <= 0) {                                     // padding rows of the chunk: Aw must still be defined (zero)
-        const int nz = min(KG_ROWS, p.rows - r0);
+        const int nz = min(KGD_ROWS, p.rows - r0);
         if (p.Aw) for (int r = 0; r < nz; r++) p.Aw[(long long)(r0 + r) * p.ld + m] = 0.0;
         return;
     }
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
             if (d < p.D) { double df = sx[r][d] - z[d]; s1[d] = fma(G, df, s1[d]); q[d] = fma(G * df, df, q[d]); }
         }
     }
-    if (p.Aw) for (int r = nr; r < min(KG_ROWS, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
+    if (p.Aw) for (int r = nr; r < min(KGD_ROWS, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
     if (p.cmaxA) {
         atomicMax(p.cmaxA + m, (unsigned long long)__double_as_longlong(mxa));
         atomicMax(p.cmaxAw + m, (unsigned long long)__double_as_longlong(mxw));
