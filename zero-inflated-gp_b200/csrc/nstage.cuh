@@ -201,8 +201,15 @@ struct KgradArgs {
     unsigned long long* cmaxA; unsigned long long* cmaxAw;   // int8 engine: per-column max |A|, max |gv A| over the chunk (bit patterns)
 };
 
+#ifndef ZIGP_KG_UNROLL
+#define ZIGP_KG_UNROLL 4          // with 8 resident blocks per SM (64 registers) the shorter unroll is the faster one (profiles/tune_r01_c.txt)
+#endif
+#ifndef ZIGP_KG_MINB
+#define ZIGP_KG_MINB 8
+#endif
+constexpr int KG_UNROLL = ZIGP_KG_UNROLL;
 template <int DT>
-__global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
+__global__ void __launch_bounds__(128, (DT <= 4 ? ZIGP_KG_MINB : 1)) kgrad_kernel(const KgradArgs p) {
     __shared__ double sx[KGD_ROWS][DT];
     __shared__ double sgm[KGD_ROWS], sgv[KGD_ROWS];
     const int m = blockIdx.x * 128 + threadIdx.x;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(128) kgrad_kernel(const KgradArgs p) {
     const double* Kp = p.K + (long long)r0 * p.ld + m;
     const double* Yp = p.Y + (long long)r0 * p.ld + m;
     double* Awp = p.Aw + (long long)r0 * p.ld + m;
-#pragma unroll 8
+#pragma unroll KG_UNROLL
     for (int r = 0; r < nr; r++) {
         const double k = Kp[(long long)r * p.ld], yy = Yp[(long long)r * p.ld], aa = Ap[(long long)r * p.ld];
         const double wa = sgv[r] * aa;

@@ -204,13 +204,15 @@ __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restric
                                                           long long plane_stride, double* __restrict__ scale,
                                                           const double* __restrict__ rowweight, const unsigned long long* __restrict__ colmax2,
                                                           int8_t* __restrict__ planes2, double* __restrict__ scale2) {
-    // 64 (n) x 32 (columns) tile, 128 threads, 17 KB of shared memory: fits beside a persistent contraction CTA
-    __shared__ double tile[64][33];
+    // 64 (n) x 32 (columns) tile, 128 threads, 16 KB of shared memory: fits beside a persistent contraction CTA.  Element (r, cc) sits at
+    // column cc ^ 8 (r / 16): the transposing read below (8 columns x 4 row groups per warp) then touches every 8-byte bank exactly twice.
+    // blockIdx.x runs over the n tiles, so blocks that are resident together write adjacent 64-byte pieces of the same plane rows.
+    __shared__ double tile[64][32];
     __shared__ double sw[64];
-    const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 64;
+    const int c0 = blockIdx.y * 32, n0 = blockIdx.x * 64;
     for (int e = threadIdx.x; e < 64 * 32; e += 128) {
         const int r = e >> 5, cc = e & 31;
-        tile[r][cc] = X[(long long)(n0 + r) * ld + c0 + cc];
+        tile[r][cc ^ ((r >> 4) << 3)] = X[(long long)(n0 + r) * ld + c0 + cc];
     }
     if (rowweight && threadIdx.x < 64) sw[threadIdx.x] = rowweight[n0 + threadIdx.x];
     __syncthreads();
@@ -221,14 +223,14 @@ __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restric
         int e = 0;
         if (mx > 0.0) e = ilogb(mx) + EOFF;
         const double inv = scalbn(1.0, -e);
-        if (blockIdx.y == 0 && grp == 0) (pass ? scale2 : scale)[c0 + cc] = scalbn(1.0, e);
+        if (blockIdx.x == 0 && grp == 0) (pass ? scale2 : scale)[c0 + cc] = scalbn(1.0, e);
         int8_t* out = (pass ? planes2 : planes) + (long long)(c0 + cc) * n + n0 + grp * 16;
         uint32_t w[NS][4];
 #pragma unroll
         for (int p = 0; p < NS; p++) { w[p][0] = 0; w[p][1] = 0; w[p][2] = 0; w[p][3] = 0; }
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            double x = tile[grp * 16 + j][cc];
+            double x = tile[grp * 16 + j][cc ^ (grp << 3)];
             if (pass) x *= sw[grp * 16 + j];
             int d[NS];
             slice_digits<NS>(x * inv, d);
@@ -679,7 +681,7 @@ inline cudaError_t launch_kgen_sliced(int ns, const double* X, const double* Z, 
 inline cudaError_t launch_slice_cols_pair(int ns, const double* X, long long ld, int n, int m, const double* w, const unsigned long long* colmaxX,
                                           const unsigned long long* colmaxWX, int8_t* planesX, int8_t* planesWX, long long plane_stride,
                                           double* scaleX, double* scaleWX, cudaStream_t st) {
-    const dim3 grid(m / 32, n / 64);
+    const dim3 grid(n / 64, m / 32);
     if (ns == NS64) slice_cols_kernel<NS64><<<grid, 128, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
     else if (ns == NS32) slice_cols_kernel<NS32><<<grid, 128, 0, st>>>(X, ld, n, m, colmaxX, planesX, plane_stride, scaleX, w, colmaxWX, planesWX, scaleWX);
     else return cudaErrorInvalidValue;
