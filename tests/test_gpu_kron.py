@@ -186,3 +186,31 @@ def test_kron_comparison_models_against_oracle(model):
     got = m.build_predict(X[:40])
     assert np.allclose(got[0].cpu().numpy(), ref[0], rtol=1e-9, atol=1e-11) and np.allclose(got[1].cpu().numpy(), ref[1], rtol=1e-9, atol=1e-11)
     assert abs(float(m.build_prior_kl()) - kl) <= 1e-10 * abs(kl)
+
+
+def test_kron_full_grid_properties_at_scale():
+    """BASELINE.json configs[4]'s inducing grid (64 x 64, M = 4096) at N = 2^23 points per evaluation, far beyond the oracle: the data term
+    is additive over the halves of the data, ELBO and packed gradient do not depend on the row order, repeated evaluations are bit-identical"""
+    N, Ms, Mt = 1 << 23, 64, 64
+    X, Y = synth.make_data(N, 3, seed=12)
+    p = synth.make_kron_params(Ms, Mt, 2, 1, seed=12)
+
+    def run(Xs, Ys):
+        m = build(Xs, Ys, p)
+        m.build_likelihood()
+        out = m._last_out.cpu().numpy().copy()
+        m.build_likelihood()
+        assert np.array_equal(out, m._last_out.cpu().numpy())
+        del m
+        torch.cuda.empty_cache()
+        return out
+    o_all = run(X, Y)
+    assert o_all[3] == 0 and np.all(np.isfinite(o_all))
+    h = N // 2
+    o_a, o_b = run(X[:h], Y[:h]), run(X[h:], Y[h:])
+    assert abs((o_a[1] + o_b[1]) - o_all[1]) <= 1e-12 * abs(o_all[1])
+    assert abs(o_a[2] - o_all[2]) <= 1e-14 * abs(o_all[2])
+    perm = np.random.default_rng(0).permutation(N)
+    o_p = run(X[perm], Y[perm])
+    assert abs(o_p[0] - o_all[0]) <= 1e-12 * abs(o_all[0])
+    assert np.linalg.norm(o_p[4:] - o_all[4:]) <= 1e-10 * np.linalg.norm(o_all[4:])

@@ -219,3 +219,36 @@ def test_size_independent_properties_at_scale():
     _, o_p, _, _ = evaluate(X[perm], Y[perm], p)
     assert abs(o_p[0] - o_all[0]) <= 1e-12 * abs(o_all[0])
     assert relnorm(o_p[4:], o_all[4:]) <= 1e-11
+
+
+def test_full_size_properties_n_2p24_m_1024():
+    """BASELINE.json configs[3] at its full size (N = 2^24, M = 1024 per latent, D = 3), where no oracle can follow: the data term is
+    additive over the two halves of the data, the ELBO and the packed gradient do not depend on the order of the rows (a permutation moves
+    every point to another chunk and another tile), and the evaluation is bit-reproducible."""
+    N, M, D = 1 << 24, 1024, 3
+    rng = np.random.default_rng(5)
+    X = rng.random((N, D))
+    on = (3.0 * np.cos(4.0 * np.pi * np.linalg.norm(X - 0.5, axis=1)) + rng.standard_normal(N)) > 0
+    Y = np.where(on, np.sin(2 * np.pi * X).sum(1) + 0.1 * rng.standard_normal(N), 0.0).reshape(-1, 1)
+    p = synth.make_params(M, M, D, 5)
+
+    def run(Xs, Ys):
+        m = synth.build_model(Xs, Ys, p)
+        m.build_likelihood()
+        out = m._last_out.cpu().numpy().copy()
+        m.build_likelihood()
+        again = m._last_out.cpu().numpy()
+        assert np.array_equal(out, again)                     # same launch sequence, no floating-point atomics
+        del m
+        torch.cuda.empty_cache()
+        return out
+    o_all = run(X, Y)
+    assert o_all[3] == 0 and np.all(np.isfinite(o_all))
+    h = N // 2
+    o_a, o_b = run(X[:h], Y[:h]), run(X[h:], Y[h:])
+    assert abs((o_a[1] + o_b[1]) - o_all[1]) <= 1e-12 * abs(o_all[1])
+    assert abs(o_a[2] - o_all[2]) <= 1e-14 * abs(o_all[2])   # the KL does not see the data
+    perm = rng.permutation(N)
+    o_p = run(X[perm], Y[perm])
+    assert abs(o_p[0] - o_all[0]) <= 1e-12 * abs(o_all[0])
+    assert relnorm(o_p[4:], o_all[4:]) <= 1e-10
