@@ -9,5 +9,5 @@ timeout 400 python bench.py --workload kron --points 67108864 --no-cpu-baseline 
 # profiler passes (after the same command exited 0 above without ncu)
 timeout 300 python bench.py --points 131072 --steps 1 --warmup 3 --no-cpu-baseline --chunk 65536 > /dev/null && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/final/launches.csv python bench.py --points 131072 --steps 1 --warmup 3 --no-cpu-baseline --chunk 65536 > gpurun_out/final/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 12 -c 4 -o gpurun_out/final/int8_gemm -f python bench.py --points 131072 --steps 1 --warmup 3 --no-cpu-baseline --chunk 65536 > gpurun_out/final/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 8 -c 8 -o gpurun_out/final/int8_gemm -f python bench.py --points 131072 --steps 1 --warmup 3 --no-cpu-baseline --chunk 65536 > gpurun_out/final/ncu_full.log 2>&1
 ls -la gpurun_out/final
