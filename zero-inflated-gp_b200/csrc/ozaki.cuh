@@ -48,7 +48,12 @@ constexpr int MAX_ACC_K = 16384;              // longest contraction accumulated
 constexpr int OBM = 128, OBN = 64;            // tile rows, tile columns
 constexpr int UK = 32;                        // k depth of one tcgen05.mma kind::i8 (bytes == int8 elements)
 constexpr int OBK = 64;                       // k bytes per pipeline stage == TMA swizzle span (32-byte rows are delivery-bound)
-constexpr int OZ_THREADS = 320;               // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quarter)
+#ifndef ZIGP_OZ_EH
+#define ZIGP_OZ_EH 2          // 4 (16 epilogue warps) shortens the write phase 10.8k -> 6.7k cycles but not the drain, and slows the MMA phase: no gain
+#endif
+constexpr int EH = ZIGP_OZ_EH;                 // epilogue warps per TMEM lane quarter; each takes CW = 64 / EH columns of its 32 rows
+constexpr int CW = OBN / EH, NCH = CW / 16;
+constexpr int OZ_THREADS = 64 + 128 * EH;     // warp 0: TMA, warp 1: MMA + TMEM alloc, then 4 EH epilogue warps
 
 template <int NS>
 struct Cfg {
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     uint64_t* tmem_full = bars + 2 * OSTAGES;
     uint64_t* tmem_empty = bars + 2 * OSTAGES + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OSTAGES + 2);
-    __shared__ double sstat[2][2][OBM];     // [half][sq / dot][row]: the two epilogue warps of a row combine their column halves
+    __shared__ double sstat[EH][2][OBM];    // [column group][sq / dot][row]: the epilogue warps of a row combine their column groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (CL > 1) ? tc05::cluster_ctarank() : 0u;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         if (lane == 0) {
             for (int s = 0; s < OSTAGES; s++) { tc05::mbar_init(&full[s], 1); tc05::mbar_init(&empty[s], CL); }
             tc05::mbar_init(tmem_full, 1);
-            tc05::mbar_init(tmem_empty, 8);
+            tc05::mbar_init(tmem_empty, 4 * EH);
             tc05::fence_barrier_init();
         }
         __syncwarp();
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             }
         }
     } else {
-        // ===== epilogue: TMEM -> fp64; warps 2-5 take columns [0,32), warps 6-9 columns [32,64) of their lane quarter =====
+        // ===== epilogue: TMEM -> fp64; warp 2 + 4 h + q drains columns [h CW, h CW + CW) of lane quarter q =====
         const int q = warp & 3, h = (warp - 2) >> 2;
         const int rl = q * 32 + lane;
         uint32_t ti = 0;
@@ -440,19 +445,19 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             const int tc = col0 / OBN;
             // this lane's column scale, dot-vector entry and row scale, requested while the MMAs of the tile are still running; the epilogue
             // broadcasts them by shuffle (a global load issued after the accumulators arrive waits ~2000 cycles behind the MMA's operand traffic)
-            const double cs_l = __ldg(g.cscale + col0 + h * 32 + lane);
-            const double dv_l = g.dotvec ? __ldg(g.dotvec + col0 + h * 32 + lane) : 0.0;
+            const double cs_l = __ldg(g.cscale + col0 + h * CW + (lane & (CW - 1)));
+            const double dv_l = g.dotvec ? __ldg(g.dotvec + col0 + h * CW + (lane & (CW - 1))) : 0.0;
             const double rs = g.rscale[r] * INVB2;
             if (warp == 2 && lane == 0) OZ_TRACE(ti, 2);
             tc05::mbar_wait(tmem_full, ti & 1u);
             tc05::fence_after_thread_sync();
             if (warp == 2 && lane == 0) OZ_TRACE(ti, 3);
-            double acc[2][16];
+            double acc[NCH][16];
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
+            for (int ch = 0; ch < NCH; ch++) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) acc[ch][j] = 0.0;
-                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32 + ch * 16);
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * CW + ch * 16);
                 if (NS & 1) {                              // odd slice count: the top weight alone
                     uint32_t v0[16];
                     tc05::tmem_ld16(ta + (uint32_t)((NS - 1) * OBN), v0);
@@ -492,17 +497,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 sl_inv = scalbn(1.0, -e);
                 const double sc = scalbn(1.0, e);
                 if (g.sl_rscale && col0 == 0 && h == 0) g.sl_rscale[r] = sc;
-                if (g.sl_cscale && row0 == 0 && q == 0) g.sl_cscale[col0 + h * 32 + lane] = sc;
+                if (g.sl_cscale && row0 == 0 && q == 0 && lane < CW) g.sl_cscale[col0 + h * CW + lane] = sc;
             }
-            uint32_t wr[2][NS][4];
+            uint32_t wr[NCH][NS][4];
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
+            for (int ch = 0; ch < NCH; ch++) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) acc[ch][j] = g.alpha * (acc[ch][j] * rs * __shfl_sync(0xffffffffu, cs_l, ch * 16 + j));
             }
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                const int c = col0 + h * 32 + ch * 16;
+            for (int ch = 0; ch < NCH; ch++) {
+                const int c = col0 + h * CW + ch * 16;
 #pragma unroll
                 for (int p = 0; p < NS; p++) { wr[ch][p][0] = 0; wr[ch][p][1] = 0; wr[ch][p][2] = 0; wr[ch][p][3] = 0; }
 #pragma unroll
@@ -546,22 +551,29 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                 }
             }
             if (reslice && g.sl_rows) {
-                int8_t* orow = g.sl_rows + (long long)r * g.cols + col0 + h * 32;
+                int8_t* orow = g.sl_rows + (long long)r * g.cols + col0 + h * CW;
 #pragma unroll
-                for (int p = 0; p < NS; p++)
-                    tc05::st_global_b32x8(orow + (long long)p * g.sl_stride, make_uint4(wr[0][p][0], wr[0][p][1], wr[0][p][2], wr[0][p][3]),
-                                          make_uint4(wr[1][p][0], wr[1][p][1], wr[1][p][2], wr[1][p][3]));
+                for (int p = 0; p < NS; p++) {
+                    if (NCH == 2)
+                        tc05::st_global_b32x8(orow + (long long)p * g.sl_stride, make_uint4(wr[0][p][0], wr[0][p][1], wr[0][p][2], wr[0][p][3]),
+                                              make_uint4(wr[NCH - 1][p][0], wr[NCH - 1][p][1], wr[NCH - 1][p][2], wr[NCH - 1][p][3]));
+                    else
+                        *reinterpret_cast<uint4*>(orow + (long long)p * g.sl_stride) = make_uint4(wr[0][p][0], wr[0][p][1], wr[0][p][2], wr[0][p][3]);
+                }
             }
             if (warp == 2 && lane == 0) OZ_TRACE(ti - 1, 5);
             if (g.stat_sq) {
-                // combine the two column halves of a row (fixed order -> deterministic); named barrier of the 256 epilogue threads
+                // combine the column groups of a row (fixed order -> deterministic); named barrier of the epilogue threads
                 sstat[h][0][rl] = ssq; sstat[h][1][rl] = sdt;
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                asm volatile("bar.sync 1, %0;\n" ::"n"(128 * EH) : "memory");
                 if (h == 0) {
-                    g.stat_sq[(long long)tc * g.rows + r] = sstat[0][0][rl] + sstat[1][0][rl];
-                    if (g.stat_dot) g.stat_dot[(long long)tc * g.rows + r] = sstat[0][1][rl] + sstat[1][1][rl];
+                    double t0 = sstat[0][0][rl], t1 = sstat[0][1][rl];
+#pragma unroll
+                    for (int e = 1; e < EH; e++) { t0 += sstat[e][0][rl]; t1 += sstat[e][1][rl]; }
+                    g.stat_sq[(long long)tc * g.rows + r] = t0;
+                    if (g.stat_dot) g.stat_dot[(long long)tc * g.rows + r] = t1;
                 }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                asm volatile("bar.sync 1, %0;\n" ::"n"(128 * EH) : "memory");
             }
         }
     }
