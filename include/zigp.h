@@ -87,6 +87,10 @@ int zigp_set_data_host(zigp_ctx* ctx, const double* X_host, const double* Y_host
 
 /* ELBO + gradient on one GPU (= accumulate + finish below).  build_likelihood + tf.gradients. */
 int zigp_elbo_grad_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
+/* Replay one evaluation as a CUDA graph (off by default): zigp_elbo_grad_dev captures its launch sequence the first time it sees a
+ * (theta, out, data, size, scale, engine) combination and replays it afterwards -- for minibatch-sized problems, where ~150 kernel launches
+ * dominate the step.  Pointers must stay valid and fixed between calls; any change re-captures.  No reference counterpart (TF1 session.run). */
+int zigp_set_graph(zigp_ctx* ctx, int on);
 int zigp_elbo_grad_host(zigp_ctx* ctx, const double* theta_host, double* out_host, void* stream);
 
 /* Data-parallel form.  accumulate: M-stage forward + the pass over this rank's points; leaves the per-shard partial

@@ -111,6 +111,11 @@ struct zigp_ctx {
     int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
     // second stream for latent g (the int8 contractions of one latent overlap the fp64 / memory-bound kernels of the other)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // CUDA-graph replay of one whole evaluation (zigp_set_graph): the launch sequence of zigp_elbo_grad_dev depends only on the pointers and
+    // sizes below, so it is captured once on `cap` and replayed -- a minibatch step of the reference's size is launch-bound (~150 kernels)
+    bool graph_on = false;
+    cudaStream_t cap = nullptr; cudaGraphExec_t gexec = nullptr; long long graph_launches = 0;
+    struct GraphKey { const void *theta, *out, *X, *Y; long long n_local; double scale; int engine, ns; } gkey{};
     // scratch of zigp_debug_gemm (int8 engine)
     int8_t *dbg_pa = nullptr, *dbg_pb = nullptr; double *dbg_sa = nullptr, *dbg_sb = nullptr;
     size_t dbg_cap_a = 0, dbg_cap_b = 0, dbg_cap_r = 0, dbg_cap_c = 0;
@@ -856,6 +861,8 @@ int zigp_destroy(zigp_ctx* c) {
     if (c->Yown) cudaFree(c->Yown);
     cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
     if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    if (c->cap) cudaStreamDestroy(c->cap);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->theta_pin) cudaFreeHost(c->theta_pin);
@@ -916,10 +923,50 @@ int zigp_finish_dev(zigp_ctx* c, const double* theta, double* out, void* stream)
     return do_finish(c, theta, out, (cudaStream_t)stream);
 }
 
+int zigp_set_graph(zigp_ctx* c, int on) {
+    if (!c) return ZIGP_EINVAL;
+    CK(cudaSetDevice(c->device));
+    if (on && !c->cap) CK(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
+    if (!on && c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+    c->graph_on = on != 0;
+    return ZIGP_OK;
+}
+
 int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
     if (!c || !theta || !out) return ZIGP_EINVAL;
-    RUN(do_accumulate(c, theta, (cudaStream_t)stream));
-    return do_finish(c, theta, out, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->graph_on && !c->profiling && c->has_data) {
+        CK(cudaSetDevice(c->device));
+        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns};
+        if (!c->gexec || memcmp(&key, &c->gkey, sizeof key) != 0) {
+            // (re)capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
+            if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+            const long long l0 = c->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(c->cap, cudaStreamCaptureModeRelaxed));
+            int r = do_accumulate(c, theta, c->cap);
+            if (r == ZIGP_OK) r = do_finish(c, theta, out, c->cap);
+            const cudaError_t ec = cudaStreamEndCapture(c->cap, &graph);
+            if (r != ZIGP_OK || ec != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (r != ZIGP_OK) return r;
+                c->err = std::string("zigp: stream capture failed: ") + cudaGetErrorString(ec);
+                return ZIGP_ECUDA;
+            }
+            const cudaError_t ei = cudaGraphInstantiate(&c->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) { c->gexec = nullptr; c->err = std::string("zigp: cudaGraphInstantiate: ") + cudaGetErrorString(ei); return ZIGP_ECUDA; }
+            c->graph_launches = c->launches - l0;
+            c->launches = l0;
+            c->gkey = key;
+        }
+        CK(cudaGraphLaunch(c->gexec, st));
+        c->launches += c->graph_launches;
+        return ZIGP_OK;
+    }
+    RUN(do_accumulate(c, theta, st));
+    return do_finish(c, theta, out, st);
 }
 
 int zigp_elbo_grad_host(zigp_ctx* c, const double* theta, double* out, void* stream) {

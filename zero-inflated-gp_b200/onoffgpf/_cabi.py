@@ -37,6 +37,7 @@ SYMBOLS = {
     "zigp_get_engine": (C.c_int, [C.c_void_p]),
     "zigp_int8_config": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "zigp_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "zigp_set_graph": (C.c_int, [C.c_void_p, C.c_int]),
     "zigp_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "zigp_launch_count": (C.c_int64, [C.c_void_p]),
@@ -79,6 +80,18 @@ def check(ctx, rc):
     raise ZigpError("%s (code %d)" % (msg, rc))
 
 
+GRAPH_MAX_ROWS = 65536
+
+
+def graph_default(graph, batch_rows, distributed):
+    """whether a model replays its evaluations as a CUDA graph: explicit argument, else ZIGP_GRAPH, else on for minibatch-sized problems"""
+    if distributed:
+        return False                  # the all-reduce sits between the two halves of the evaluation
+    if graph is None and os.environ.get("ZIGP_GRAPH") is not None:
+        graph = os.environ["ZIGP_GRAPH"] not in ("0", "")
+    return bool(graph) if graph is not None else batch_rows <= GRAPH_MAX_ROWS
+
+
 class Context:
     """Owns one zigp_ctx (one GPU)."""
 
@@ -97,11 +110,11 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            h, self._h = self._h, None
             try:
-                lib().zigp_destroy(self._h)
-            except Exception:       # interpreter shutdown: the module globals may already be gone
+                lib().zigp_destroy(h)
+            except Exception:       # interpreter shutdown: the module globals (ctypes, lib) may already be gone
                 pass
-            self._h = C.c_void_p()
 
     __del__ = close
 
@@ -129,6 +142,21 @@ class Context:
     def set_precision(self, precision):
         """'fp64' (7 x 8-bit slices) or 'fp32' (4 x 8-bit slices: reduced precision, rel 1e-4 class) -- int8 engine only"""
         self.call("zigp_set_precision", self.PRECISIONS[precision] if isinstance(precision, str) else int(precision))
+
+    def set_graph(self, on: bool):
+        """replay whole evaluations as one CUDA graph (zigp_set_graph): for minibatch-sized problems, where kernel launches dominate"""
+        self.call("zigp_set_graph", int(bool(on)))
+        self._g_theta = self._g_out = None
+
+    def evaluate_graph(self, theta, stream):
+        """zigp_elbo_grad_dev on context-lifetime buffers (fixed pointers, so the captured graph is replayed); returns a copy of `out`"""
+        import torch
+        if getattr(self, "_g_theta", None) is None or self._g_theta.device != theta.device:
+            self._g_theta = torch.empty(self.theta_len, dtype=torch.float64, device=theta.device)
+            self._g_out = torch.empty(self.out_len, dtype=torch.float64, device=theta.device)
+        self._g_theta.copy_(theta.reshape(-1))
+        self.call("zigp_elbo_grad_dev", self._g_theta.data_ptr(), self._g_out.data_ptr(), stream)
+        return self._g_out.clone()
 
     def int8_config(self):
         """(slices per operand, bits per slice, int8 slice products per product) of the int8 engine of this context"""

@@ -82,12 +82,13 @@ class OnOffSVGP(Parameterized):
     - kernf, kerng are RBF kernel objects for the f (magnitude) and g (on/off) processes
     - Zf, Zg are inducing point locations, Mf x D and Mg x D
     Extra keyword arguments (not in the reference): device, jitter, chunk_rows, distributed, engine ('int8' | 'dmma'),
-    precision ('fp64' | 'fp32').
+    precision ('fp64' | 'fp32'), graph (replay each evaluation as one CUDA graph; default: on for batches of at most 65536 points, where
+    the ~150 kernel launches of an evaluation dominate; ZIGP_GRAPH=0/1 overrides).
     """
 
     def __init__(self, X, Y, kernf, kerng, likelihood, Zf, Zg, mean_function=None, minibatch_size=None, name="model",
                  device=None, jitter=JITTER_LEVEL, chunk_rows=None, distributed=False, engine=None, precision=None,
-                 whiten=False, q_diag=True):
+                 whiten=False, q_diag=True, graph=None):
         if not torch.cuda.is_available():
             raise _cabi.ZigpError("OnOffSVGP needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _cabi.lib()  # fail loudly now if the extension is missing
@@ -151,6 +152,9 @@ class OnOffSVGP(Parameterized):
         self.precision = precision or os.environ.get("ZIGP_PRECISION", "fp64")
         if self.precision != "fp64":
             self._ctx.set_precision(self.precision)
+        self._graph = _cabi.graph_default(graph, min(self.minibatch_size, self.num_data_local), distributed)
+        if self._graph:
+            self._ctx.set_graph(True)
         self._chunk_rows = int(chunk_rows)
         self.jitter = float(jitter)
         for p in self._theta_params():
@@ -189,7 +193,14 @@ class OnOffSVGP(Parameterized):
             self._Xb, self._Yb = self._X_dev, self._Y_dev
         else:
             it = torch.as_tensor(idx, device=self.device)
-            self._Xb, self._Yb = self._X_dev[it].contiguous(), self._Y_dev[it].contiguous()
+            if getattr(self, "_graph", False) and getattr(self, "_Xb_buf", None) is not None and self._Xb_buf.shape[0] == it.numel():
+                torch.index_select(self._X_dev, 0, it, out=self._Xb_buf)       # fixed batch buffers: the captured graph keeps its pointers
+                torch.index_select(self._Y_dev, 0, it, out=self._Yb_buf)
+                self._Xb, self._Yb = self._Xb_buf, self._Yb_buf
+            else:
+                self._Xb, self._Yb = self._X_dev[it].contiguous(), self._Y_dev[it].contiguous()
+                if getattr(self, "_graph", False):
+                    self._Xb_buf, self._Yb_buf = self._Xb, self._Yb
         n_b = self._Xb.shape[0]
         n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
         scale = float(self.num_data) / float(n_global)        # onoffgpf/OnOffSVGP.py:119-120
@@ -200,8 +211,11 @@ class OnOffSVGP(Parameterized):
         with torch.cuda.device(self.device):
             theta = theta.contiguous()
             self._next_batch()
-            out = torch.empty(self._ctx.out_len, dtype=DTYPE, device=self.device)
             st = self._stream()
+            if getattr(self, "_graph", False) and not self.distributed:
+                out = self._ctx.evaluate_graph(theta, st)
+                return self._check_out(out)
+            out = torch.empty(self._ctx.out_len, dtype=DTYPE, device=self.device)
 
             def accumulate():
                 self._ctx.call("zigp_accumulate_dev", theta.data_ptr(), st)
@@ -215,13 +229,16 @@ class OnOffSVGP(Parameterized):
                 parallel.evaluate_sharded(accumulate, finish)
             else:
                 finish(accumulate())
-            info = int(out[3].item())
-            if info != 0:
-                k = info - 1
-                raise _cabi.NotPositiveDefiniteError("Kmm + jitter*I of latent %s is not positive definite (pivot %d)"
-                                                     % ("g" if (k >> 20) else "f", k & ((1 << 20) - 1)))
-            self._last_out = out
-            return out
+            return self._check_out(out)
+
+    def _check_out(self, out):
+        info = int(out[3].item())
+        if info != 0:
+            k = info - 1
+            raise _cabi.NotPositiveDefiniteError("Kmm + jitter*I of latent %s is not positive definite (pivot %d)"
+                                                 % ("g" if (k >> 20) else "f", k & ((1 << 20) - 1)))
+        self._last_out = out
+        return out
 
     # -- reference API ----------------------------------------------------------------------------------------
     def build_likelihood(self) -> torch.Tensor:
@@ -351,6 +368,8 @@ class OnOffSVGP(Parameterized):
         self._ctx.set_engine(getattr(self, "engine", "int8"))
         if getattr(self, "precision", "fp64") != "fp64":
             self._ctx.set_precision(self.precision)
+        if getattr(self, "_graph", False):
+            self._ctx.set_graph(True)
         self._last_out = None
 
     # -- host-buffer entry (bench.py e2e; the call a non-torch binding would make) -----------------------------

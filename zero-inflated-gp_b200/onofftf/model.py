@@ -74,7 +74,7 @@ class OnOffKron(Parameterized):
     variances; flattened inducing index m = i_space * Mt + i_time."""
 
     def __init__(self, X, Y, Zf_list, Zg_list, fkell, fkvar, gkell, gkvar, noisevar=0.01, u_fm=None, u_fs_sqrt=None, u_gm=None,
-                 u_gs_sqrt=None, num_minibatch=None, jitter=JITTER_LEVEL, device=None, chunk_rows=None, distributed=False, seed=121):
+                 u_gs_sqrt=None, num_minibatch=None, jitter=JITTER_LEVEL, device=None, chunk_rows=None, distributed=False, seed=121, graph=None):
         if not torch.cuda.is_available():
             raise _cabi.ZigpError("OnOffKron needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _cabi.lib()
@@ -124,6 +124,9 @@ class OnOffKron(Parameterized):
             chunk_rows = min(DEFAULT_CHUNK_ROWS, (rows + 511) // 512 * 512)
         self._ctx = _cabi.Context(self.device.index or 0, 0, 0, 0, self.jitter, chunk_rows,
                                   kron=(self.num_inducing_f[0], self.num_inducing_f[1], self.num_inducing_g[0], self.num_inducing_g[1], self.Ds, self.Dt))
+        self._graph = _cabi.graph_default(graph, rows, self.distributed)      # minibatch steps are launch-bound: replay them as one CUDA graph
+        if self._graph:
+            self._ctx.set_graph(True)
         for p in self._theta_params():
             p.to(self.device)
         self._last_out = None
@@ -161,8 +164,14 @@ class OnOffKron(Parameterized):
             self._Xb, self._Yb = self._X_dev, self._Y_dev
         else:
             xb, yb = self._data.next_batch(self.num_minibatch)          # scripts/onoff.py:377
-            self._Xb = torch.as_tensor(np.ascontiguousarray(xb)).to(self.device)
-            self._Yb = torch.as_tensor(np.ascontiguousarray(yb)).reshape(-1).to(self.device)
+            xh, yh = torch.as_tensor(np.ascontiguousarray(xb)), torch.as_tensor(np.ascontiguousarray(yb)).reshape(-1)
+            if getattr(self, "_graph", False) and getattr(self, "_Xb_buf", None) is not None and self._Xb_buf.shape == xh.shape:
+                self._Xb_buf.copy_(xh); self._Yb_buf.copy_(yh)                 # fixed batch buffers: the captured graph keeps its pointers
+                self._Xb, self._Yb = self._Xb_buf, self._Yb_buf
+            else:
+                self._Xb, self._Yb = xh.to(self.device), yh.to(self.device)
+                if getattr(self, "_graph", False):
+                    self._Xb_buf, self._Yb_buf = self._Xb, self._Yb
         n_b = self._Xb.shape[0]
         n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
         scale = float(self.num_data) / float(n_global)                   # scripts/onoff.py:311
@@ -172,8 +181,11 @@ class OnOffKron(Parameterized):
         with torch.cuda.device(self.device):
             theta = theta.contiguous()
             self._next_batch()
-            out = torch.empty(self._ctx.out_len, dtype=DTYPE, device=self.device)
             st = self._stream()
+            if getattr(self, "_graph", False) and not self.distributed:
+                out = self._ctx.evaluate_graph(theta, st)
+                return self._check_out(out)
+            out = torch.empty(self._ctx.out_len, dtype=DTYPE, device=self.device)
 
             def accumulate():
                 self._ctx.call("zigp_accumulate_dev", theta.data_ptr(), st)
@@ -187,14 +199,17 @@ class OnOffKron(Parameterized):
                 parallel.evaluate_sharded(accumulate, finish)
             else:
                 finish(accumulate())
-            info = int(out[3].item())
-            if info != 0:
-                k = info - 1
-                tag = k >> 20
-                raise _cabi.NotPositiveDefiniteError("Kmm + jitter*I of latent %s, %s factor, is not positive definite (pivot %d)"
-                                                     % ("g" if (tag >> 1) else "f", "time" if (tag & 1) else "space", k & ((1 << 20) - 1)))
-            self._last_out = out
-            return out
+            return self._check_out(out)
+
+    def _check_out(self, out):
+        info = int(out[3].item())
+        if info != 0:
+            k = info - 1
+            tag = k >> 20
+            raise _cabi.NotPositiveDefiniteError("Kmm + jitter*I of latent %s, %s factor, is not positive definite (pivot %d)"
+                                                 % ("g" if (tag >> 1) else "f", "time" if (tag & 1) else "space", k & ((1 << 20) - 1)))
+        self._last_out = out
+        return out
 
     # -- the script's closures as methods ----------------------------------------------------------------------------
     def build_likelihood(self) -> torch.Tensor:
