@@ -329,7 +329,7 @@ def run_ours(a):
     achieved = flops_per_launch / (gemm_ms / max(1, gemm_n) * 1e-3) * 1e-12 if gemm_n else 0.0
     int8 = (not kron) and getattr(m, "engine", "dmma") == "int8"
     if int8:
-        # int8 engine: per chunk and latent three launches of ozaki_gemm_kernel_v2 (A = K T^T lower, |R A|^2 upper, Y = G A full) =
+        # int8 engine: per chunk and latent three launches of ozaki_gemm_kernel (A = K T^T lower, |R A|^2 upper, Y = G A full) =
         # 4 M^2 fp64-equivalent flop per point per latent; each fp64 product is NSL (NSL + 1) / 2 int8 slice products
         gflop = 2.0 * 4.0 * float(M) * M * n_loc
         achieved = gflop / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else 0.0
@@ -391,7 +391,7 @@ def measured_peaks():
 
 def roofline_head(int8, kron, achieved, dgemm_tf, M, m):
     """the roofline block of the dominant kernel.  DMMA engine: fp64 flop/s against the cuBLAS DGEMM rate measured in this run.
-    int8 engine: the kernel executes 36 int8 slice products per fp64-equivalent product, so `achieved` is the executed int8
+    int8 engine: the kernel executes NS (NS + 1) / 2 int8 slice products per fp64-equivalent product (28 at NS = 7; zigp_int8_config), so `achieved` is the executed int8
     rate (TOP/s) against the int8 tensor peak, taken as 2 x the MEASURED bf16 rate (MEASURED_PEAKS.json has no int8 entry; the
     nominal int8 : bf16 ratio of B200 is 2); the fp64-equivalent rate and the DGEMM rate it replaces are given beside it."""
     if int8:
@@ -400,7 +400,7 @@ def roofline_head(int8, kron, achieved, dgemm_tf, M, m):
         src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a long, power-capped step)" if mp else "2 x 1400 (fallback: no MEASURED_PEAKS.json)"
         peak = 2.0 * (bf16 if bf16 else 1400.0)
         nsl, sbits, prods = m._ctx.int8_config()
-        return {"bound": "tensor", "kernel": "ozaki_gemm_kernel_v2<2> (tcgen05.mma kind::i8, 128x64 tiles, %d x %d-bit slices = %d int8 slice products per fp64 product, TMA multicast in 2-CTA clusters, persistent)" % (nsl, sbits, prods),
+        return {"bound": "tensor", "kernel": "ozaki_gemm_kernel<NS,2> (tcgen05.mma kind::i8, 128x64 tiles, %d x %d-bit slices = %d int8 slice products per fp64 product, TMA multicast in 2-CTA clusters, persistent)" % (nsl, sbits, prods),
                 "achieved": achieved * prods, "peak": peak, "unit": "TOP/s", "frac": achieved * prods / peak,
                 "traffic": traffic_per_launch(M, ctx_chunk_rows(m), "int8") if prods == 28 else None, "slice_products": prods,
                 "peak_source": src, "fp64_equivalent_tflops": achieved, "dgemm_tflops_measured": dgemm_tf,

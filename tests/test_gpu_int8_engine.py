@@ -1,4 +1,4 @@
-"""GPU tests of the int8 tensor-core contraction engine (csrc/ozaki.cuh: fp64 operands split exactly into 8 x 7-bit slices,
+"""GPU tests of the int8 tensor-core contraction engine (csrc/ozaki.cuh: fp64 operands split exactly into 7 x 8-bit slices,
 tcgen05.mma kind::i8 with int32 accumulation in TMEM, fp64 recombination) against float64 references."""
 import numpy as np
 import pytest
