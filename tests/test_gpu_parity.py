@@ -252,3 +252,28 @@ def test_full_size_properties_n_2p24_m_1024():
     o_p = run(X[perm], Y[perm])
     assert abs(o_p[0] - o_all[0]) <= 1e-12 * abs(o_all[0])
     assert relnorm(o_p[4:], o_all[4:]) <= 1e-10
+
+
+def test_graph_replay_equals_direct_launches():
+    """zigp_set_graph: the captured evaluation must be the same launch sequence -- bit-identical results, also after the parameters change
+    (the graph reads them from a fixed buffer) and with a minibatch stream (fixed batch buffers, changing contents)"""
+    N, M, D = 3000, 40, 2
+    X, Y = synth.make_data(N, D, 31)
+    p = synth.make_params(M, M, D, 31)
+    outs = {}
+    for gr in (True, False):
+        m = synth.build_model(X, Y, p, graph=gr, minibatch_size=1024)
+        assert m._graph == gr
+        seq = []
+        for it in range(4):
+            if it == 2:
+                m.kernf.lengthscales = np.asarray(p["kernf_lengthscales"]) * 1.3
+                m.u_fm = np.asarray(p["u_fm"]) + 0.05
+            m.build_likelihood()
+            seq.append(m._last_out.cpu().numpy().copy())
+        outs[gr] = seq
+        if gr:
+            assert m._ctx.launch_count() > 0
+    for a, b in zip(outs[True], outs[False]):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(outs[True][1], outs[True][2])      # the parameter change is seen by the replay
