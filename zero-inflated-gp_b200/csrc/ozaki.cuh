@@ -65,36 +65,48 @@ struct Cfg {
 };
 
 // ---- slicing ------------------------------------------------------------------------------------------------------------
-// 8 NS fractional bits of t (|t| < 1/4) as NS balanced base-256 digits, most significant first, returned as their two's-complement
-// BYTES (0..255).  The balanced digit of an integer V is its sign-extended low byte and the remaining quotient is (V + 128) >> 8,
-// so a digit costs an add and a shift.  NS = 7: round(t 2^56) does not fit the 53-bit significand; it is formed as two exact
-// 28-bit roundings h1 2^28 + h2 and regrouped into 32-bit words (hi 2^24 + lo), so the whole extraction is 32-bit integer work
-// and the roundings are additions of 1.5 2^52 whose low mantissa word is read back (F2I / I2F on doubles run at a fraction of the
-// DADD rate and made the slicing kernels conversion-bound).  NS <= 4: one rounding to 8 NS <= 32 bits.
+// 8 NS fractional bits of t (|t| < 1/4) as NS balanced base-256 digits d_p in [-128, 127], V = round(t 2^(8 NS)) = sum_p d_p 256^(NS-1-p).
+// Adding 128 to every digit position turns the balanced digits into the plain bytes of U = V + 0x80...80, so the two's-complement
+// bytes of the digits are  bytes(U) XOR 0x80 : one 64-bit add and one XOR instead of a carry chain.  Byte k of the result is digit
+// NS - 1 - k.  NS = 7: round(t 2^56) does not fit the 53-bit significand; it is formed from two exact 28-bit roundings, h1 2^28 + h2, and
+// the roundings are additions of 1.5 2^52 whose low mantissa word is read back (F2I / I2F on doubles run at a fraction of the DADD
+// rate).  NS = 4: one rounding to 32 bits.
 template <int NS>
-__device__ __forceinline__ void slice_digits(double t, int (&d)[NS]) {
-    static_assert(NS == 7 || NS <= 4, "slice_digits: 7 or <= 4 slices");
+__device__ __forceinline__ void slice_bytes(double t, uint32_t& lo, uint32_t& hi) {
+    static_assert(NS == 7 || NS == 4, "slice_bytes: 7 or 4 slices");
     if (NS == 7) {
         const double v1 = t * 268435456.0;                 // 2^28, exact
         const double s1 = v1 + RMAGIC;                     // round-to-nearest-even to an integer: |v1| < 2^31, ulp(1.5 2^52) = 1
         const int h1 = __double2loint(s1);                 // |h1| <= 2^26
         const double v2 = (v1 - (s1 - RMAGIC)) * 268435456.0;   // exact remainder, |.| <= 2^27
         const int h2 = __double2loint(v2 + RMAGIC);
-        int lo = h2 & 0xFFFFFF;                            // round(t 2^56) = hi 2^24 + lo
-        int hi = (h1 << 4) + (h2 >> 24);
-        d[NS - 1] = lo & 255; lo = (lo + 128) >> 8;
-        d[NS - 2] = lo & 255; lo = (lo + 128) >> 8;
-        d[NS - 3] = lo & 255; lo = (lo + 128) >> 8;        // carry into the upper word
-        hi += lo;
-#pragma unroll
-        for (int i = NS - 4; i >= 1; i--) { d[i] = hi & 255; hi = (hi + 128) >> 8; }
-        d[0] = hi & 255;
+        const unsigned long long U = (unsigned long long)(((long long)h1 << 28) + (long long)h2) + 0x0080808080808080ULL;
+        const unsigned long long X = U ^ 0x0080808080808080ULL;
+        lo = (uint32_t)X; hi = (uint32_t)(X >> 32);
     } else {
-        int w = __double2loint(t * (double)(1LL << (NS * SBITS)) + RMAGIC);     // |w| <= 2^(8 NS - 2)
-#pragma unroll
-        for (int i = NS - 1; i >= 1; i--) { d[i] = w & 255; w = (w + 128) >> 8; }
-        d[0] = w & 255;
+        const uint32_t w = (uint32_t)__double2loint(t * 4294967296.0 + RMAGIC);    // |w| <= 2^30
+        lo = (w + 0x80808080u) ^ 0x80808080u; hi = 0;
     }
+}
+
+// digit p of the sliced value as the byte selector of __byte_perm: (word, byte) = (hi, 2 - p) for p < 3, (lo, 6 - p) otherwise (NS = 7)
+template <int NS>
+__device__ __forceinline__ uint32_t plane_word4(int p, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
+    // bytes of plane p for four consecutive elements, element 0 in the low byte
+    const int k = NS - 1 - p;                              // byte index inside the 8-byte digit string
+    const uint32_t b = (uint32_t)(k & 3), sel = b | ((4u + b) << 4);
+    const uint32_t t01 = (k < 4) ? __byte_perm(lo[0], lo[1], sel) : __byte_perm(hi[0], hi[1], sel);
+    const uint32_t t23 = (k < 4) ? __byte_perm(lo[2], lo[3], sel) : __byte_perm(hi[2], hi[3], sel);
+    return __byte_perm(t01, t23, 0x5410);
+}
+
+// the digits as separate integers (two's-complement bytes 0..255), most significant first
+template <int NS>
+__device__ __forceinline__ void slice_digits(double t, int (&d)[NS]) {
+    uint32_t lo, hi;
+    slice_bytes<NS>(t, lo, hi);
+#pragma unroll
+    for (int p = 0; p < NS; p++) { const int k = NS - 1 - p; d[p] = (int)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 255u); }
 }
 
 // planes[p][r][k] = X_p of row r (k contiguous, plane stride in bytes), scale[r] = 2^e.  One warp per row; K % 128 == 0.
@@ -121,14 +133,11 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     for (int k = lane * 4; k < K; k += 128) {
         const double4 v = *reinterpret_cast<const double4*>(x + k);
         const double t[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
-        int d[4][NS];
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) slice_digits<NS>(t[j], d[j]);
+        for (int j = 0; j < 4; j++) slice_bytes<NS>(t[j], lo[j], hi[j]);
 #pragma unroll
-        for (int p = 0; p < NS; p++) {
-            const uint32_t pk = (uint32_t)(d[0][p] & 0xff) | ((uint32_t)(d[1][p] & 0xff) << 8) | ((uint32_t)(d[2][p] & 0xff) << 16) | ((uint32_t)(d[3][p] & 0xff) << 24);
-            *reinterpret_cast<uint32_t*>(out + (long long)p * plane_stride + k) = pk;
-        }
+        for (int p = 0; p < NS; p++) *reinterpret_cast<uint32_t*>(out + (long long)p * plane_stride + k) = plane_word4<NS>(p, lo, hi);
     }
 }
 
@@ -171,14 +180,11 @@ __global__ void __launch_bounds__(128) kgen_sliced_kernel(const double* __restri
             }
         }
         tc05::st_global_f64x4(K + (long long)r * Mp + m0, k[0], k[1], k[2], k[3]);
-        int d4[4][NS];
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) slice_digits<NS>(k[j] * inv, d4[j]);
+        for (int j = 0; j < 4; j++) slice_bytes<NS>(k[j] * inv, lo[j], hi[j]);
 #pragma unroll
-        for (int p = 0; p < NS; p++) {
-            const uint32_t pk = (uint32_t)(d4[0][p] & 0xff) | ((uint32_t)(d4[1][p] & 0xff) << 8) | ((uint32_t)(d4[2][p] & 0xff) << 16) | ((uint32_t)(d4[3][p] & 0xff) << 24);
-            *reinterpret_cast<uint32_t*>(planes + (long long)p * plane_stride + (long long)r * Mp + m0) = pk;
-        }
+        for (int p = 0; p < NS; p++) *reinterpret_cast<uint32_t*>(planes + (long long)p * plane_stride + (long long)r * Mp + m0) = plane_word4<NS>(p, lo, hi);
         if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) scale[r] = sc;
     }
 }
@@ -253,15 +259,16 @@ __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restric
             int8_t* out = (pass ? planes2 : planes) + (long long)(c0 + cc) * n + n0 + grp * 16;
             uint32_t w[NS][4];
 #pragma unroll
-            for (int p = 0; p < NS; p++) { w[p][0] = 0; w[p][1] = 0; w[p][2] = 0; w[p][3] = 0; }
+            for (int j = 0; j < 16; j += 4) {
+                uint32_t lo[4], hi[4];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                double x = tile[grp * 16 + j][cc ^ (grp << 3)];
-                if (pass) x *= sw[grp * 16 + j];
-                int d[NS];
-                slice_digits<NS>(x * (pass ? inv1 : inv0), d);
+                for (int i = 0; i < 4; i++) {
+                    double x = tile[grp * 16 + j + i][cc ^ (grp << 3)];
+                    if (pass) x *= sw[grp * 16 + j + i];
+                    slice_bytes<NS>(x * (pass ? inv1 : inv0), lo[i], hi[i]);
+                }
 #pragma unroll
-                for (int p = 0; p < NS; p++) w[p][j >> 2] |= (uint32_t)(d[p] & 0xff) << (8 * (j & 3));
+                for (int p = 0; p < NS; p++) w[p][j >> 2] = plane_word4<NS>(p, lo, hi);
             }
 #pragma unroll
             for (int p = 0; p < NS; p++) *reinterpret_cast<uint4*>(out + (long long)p * plane_stride) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
@@ -555,19 +562,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                         }
                     }
                     if (reslice) {
-                        int d[4][NS];
+                        uint32_t lo[4], hi[4];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) slice_digits<NS>(v[i] * sl_inv, d[i]);
+                        for (int i = 0; i < 4; i++) slice_bytes<NS>(v[i] * sl_inv, lo[i], hi[i]);
 #pragma unroll
-                        for (int p = 0; p < NS; p++)
-                            wr[ch][p][j >> 2] = (uint32_t)(d[0][p] & 0xff) | ((uint32_t)(d[1][p] & 0xff) << 8) | ((uint32_t)(d[2][p] & 0xff) << 16) | ((uint32_t)(d[3][p] & 0xff) << 24);
+                        for (int p = 0; p < NS; p++) wr[ch][p][j >> 2] = plane_word4<NS>(p, lo, hi);
                         if (g.sl_cols) {
                             // transposed planes: the 32 lanes of a warp are 32 consecutive rows -> one full 32-byte sector per store
                             int8_t* oc = g.sl_cols + (long long)(c + j) * g.rows + r;
 #pragma unroll
                             for (int p = 0; p < NS; p++) {
 #pragma unroll
-                                for (int i = 0; i < 4; i++) oc[(long long)p * g.sl_stride + (long long)i * g.rows] = (int8_t)d[i][p];
+                                for (int i = 0; i < 4; i++) oc[(long long)p * g.sl_stride + (long long)i * g.rows] = (int8_t)(wr[ch][p][j >> 2] >> (8 * i));
                             }
                         }
                     }
