@@ -127,3 +127,22 @@ def test_reslicing_modes_agree(monkeypatch):
         assert np.all(np.isfinite(a))
         assert abs(a[0] - ref[0]) <= 1e-12 * abs(ref[0])
         assert np.linalg.norm(a[2:] - ref[2:]) <= 1e-10 * np.linalg.norm(ref[2:])
+
+
+@pytest.mark.parametrize("M,D", [(1536, 3), (2048, 5)])
+def test_engines_agree_for_larger_inducing_sets(M, D):
+    """beyond the benchmark's M = 1024: 24 and 32 column tiles, split N > 256 instructions, D = 5 kernel tiles"""
+    N = 40_000
+    X, Y = synth.make_data(N, D, 40 + D)
+    p = synth.make_params(M, M, D, 40 + D)
+    outs = {}
+    for eng in ("dmma", "int8"):
+        m = synth.build_model(X, Y, p, engine=eng)
+        m.build_likelihood()
+        outs[eng] = m._last_out.cpu().numpy()
+        del m
+        torch.cuda.empty_cache()
+    a, b = outs["int8"], outs["dmma"]
+    assert a[3] == 0 and b[3] == 0
+    assert abs(a[0] - b[0]) <= 1e-11 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-11 * abs(b[1])
+    assert np.linalg.norm(a[4:] - b[4:]) <= 1e-9 * np.linalg.norm(b[4:])
