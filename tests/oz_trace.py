@@ -7,19 +7,23 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from onoffgpf import _cabi
 
 tri = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+mode = sys.argv[2] if len(sys.argv) > 2 else "out"          # out: fp64 output only; stat: statistics only (no output); both
 dev = torch.device("cuda:0")
 ctx = _cabi.Context(0, 64, 64, 1, 1e-6, 512)
 rows, cols, K = 65536, 1024, 1024
 In = torch.randn(rows, K, dtype=torch.float64, device=dev); W = torch.randn(cols, K, dtype=torch.float64, device=dev)
 Out = torch.empty((rows, cols), dtype=torch.float64, device=dev)
+Stat = torch.zeros((cols // 64, rows), dtype=torch.float64, device=dev)
+optr = Out.data_ptr() if mode in ("out", "both") else None
+sptr = Stat.data_ptr() if mode in ("stat", "both") else None
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
-    ctx.call("zigp_debug_gemm", 1, In.data_ptr(), K, W.data_ptr(), K, Out.data_ptr(), cols, rows, cols, K, tri, None, st)
+    ctx.call("zigp_debug_gemm", 1, In.data_ptr(), K, W.data_ptr(), K, optr, cols, rows, cols, K, tri, sptr, st)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); ctx.call("zigp_debug_gemm", 2, In.data_ptr(), K, W.data_ptr(), K, Out.data_ptr(), cols, rows, cols, K, tri, None, st); e1.record()
+e0.record(); ctx.call("zigp_debug_gemm", 2, In.data_ptr(), K, W.data_ptr(), K, optr, cols, rows, cols, K, tri, sptr, st); e1.record()
 torch.cuda.synchronize()
-print("gemm only: %.3f ms" % e0.elapsed_time(e1))
+print("tri %d mode %s gemm only: %.3f ms" % (tri, mode, e0.elapsed_time(e1)))
 lib = ctypes.CDLL(_cabi.LIB_PATH)
 buf = (ctypes.c_longlong * (8 * 256))()
 assert lib.zigp_debug_trace(buf, 8 * 256) == 0

@@ -1061,7 +1061,7 @@ int zigp_debug_buffer(zigp_ctx* c, const char* name, int latent, double** ptr, i
 
 int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, const double* W, int64_t ldw, double* Out, int64_t ldo, int rows, int cols,
                     int kdim, int tri, double* stat_sq, void* stream) {
-    if (!c || !In || !W || !Out || rows <= 0 || cols <= 0 || kdim <= 0 || tri < 0 || tri > 2) return ZIGP_EINVAL;
+    if (!c || !In || !W || (!Out && !(engine != 0 && stat_sq)) || rows <= 0 || cols <= 0 || kdim <= 0 || tri < 0 || tri > 2) return ZIGP_EINVAL;   // int8 engine: Out may be null (statistics only)
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
     if (engine == 0) {
