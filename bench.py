@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="dense", choices=["dense", "kron"],
                     help="dense: BASELINE.json configs[3] (the headline); kron: configs[4], Kronecker inducing grid Ms x Mt = 64 x 64 (secondary line)")
-    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
-                    help="fp64: the headline (matches the reference's float64); fp32: reduced-precision contractions (4 x 8-bit slices), secondary line")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32", "fp64-grad6"],
+                    help="fp64: the headline (matches the reference's float64); fp32: reduced-precision contractions (4 x 8-bit slices), secondary line; "
+                         "fp64-grad6: fp64 ELBO path, gradient-only contractions on 6 slices (secondary line)")
     ap.add_argument("--engine", default=None, choices=["int8", "dmma"])
     ap.add_argument("--ms", type=int, default=64)
     ap.add_argument("--mt", type=int, default=64)
@@ -357,7 +358,8 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if a.precision == "fp64" else "f64 storage / 32-bit sliced contractions (reduced-precision mode, not the headline)", "data": "synthetic",
+            "dtype": {"fp64": "f64", "fp32": "f64 storage / 32-bit sliced contractions (reduced-precision mode, not the headline)",
+                      "fp64-grad6": "f64, gradient-only contractions on 6 of 7 slices (mixed mode, not the headline)"}[a.precision], "data": "synthetic",
             "config": {"workload": (("BASELINE.json configs[4] (secondary line, not the headline): Kronecker inducing grid %d x %d (space x time), synthetic 2+1-D zero-inflated, N=%d, fp64" % (a.ms, a.mt, N))
                                     if kron else "BASELINE.json configs[3]: synthetic 3-D spatio-temporal zero-inflated, N=2^24 total, M=1024 per latent, RBF-ARD, fp64"
                                     if named else "synthetic zero-inflated N=%d D=%d M=%d fp64 (dev override, not the named config)" % (N, D, M)),

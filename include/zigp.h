@@ -123,7 +123,10 @@ int zigp_get_engine(const zigp_ctx* ctx);
 int zigp_int8_config(const zigp_ctx* ctx, int* slices, int* slice_bits, int* slice_products);
 /* Precision of the N-scale contractions on the int8 engine: 0 = fp64 (7 x 8-bit slices, 55 bits below each row's scale, the default;
  * results within the fp64 tolerances of the reference), 1 = reduced, fp32-class (4 x 8-bit slices, 31 bits, 10 instead of 28 slice
- * products; the M-scale stage, the likelihood and all accumulations stay fp64).  BASELINE.json's "fp32 mode", tolerance rel 1e-4. */
+ * products; the M-scale stage, the likelihood and all accumulations stay fp64).  BASELINE.json's "fp32 mode", tolerance rel 1e-4.
+ * 2 = mixed: the contractions the ELBO depends on (A = K T^T, |R A|^2) keep 7 slices, the gradient-only ones (Y = G A, the rank update) use
+ * the top 6 planes (21 products): the ELBO is bit-identical to mode 0, gradients carry 47 instead of 55 bits below each row's scale
+ * (~10 x the float64 gradient error).  Opt-in, not the default. */
 int zigp_set_precision(zigp_ctx* ctx, int mode);
 /* Test hook: one contraction Out[r,c] = sum_k In[r,k] W[c,k] (tri: 0 full, 1 lower k <= c, 2 upper k >= c; optional per-row,
  * per-64-column-tile sums of squares) through engine 0 (DMMA, csrc/gemm_f64.cuh) or engine 1 (fp64 emulated on the int8 tensor

@@ -146,3 +146,21 @@ def test_engines_agree_for_larger_inducing_sets(M, D):
     assert a[3] == 0 and b[3] == 0
     assert abs(a[0] - b[0]) <= 1e-11 * abs(b[0]) and abs(a[1] - b[1]) <= 1e-11 * abs(b[1])
     assert np.linalg.norm(a[4:] - b[4:]) <= 1e-9 * np.linalg.norm(b[4:])
+
+
+def test_mixed_mode_keeps_the_elbo_and_bounds_the_gradient_error():
+    """precision='fp64-grad6': the ELBO-path contractions stay at 7 slices (ELBO, data term and KL bit-identical to the fp64 mode), the
+    gradient-only contractions use the top 6 planes: the packed gradient stays within 1e-11 of the fp64 mode's on a well-conditioned problem"""
+    N, M, D = 70_001, 256, 3
+    X, Y = synth.make_data(N, D, 22)
+    p = synth.make_params(M, M, D, 22)
+    outs = {}
+    for prec in ("fp64", "fp64-grad6"):
+        m = synth.build_model(X, Y, p, engine="int8", precision=prec)
+        m.build_likelihood()
+        outs[prec] = m._last_out.cpu().numpy()
+        del m
+    a, b = outs["fp64-grad6"], outs["fp64"]
+    assert np.array_equal(a[:4], b[:4])
+    err = np.linalg.norm(a[4:] - b[4:]) / np.linalg.norm(b[4:])
+    assert 0 < err <= 1e-11, err

@@ -32,6 +32,7 @@ namespace zigp {
 namespace oz {
 
 constexpr int NS64 = 7;                       // slices per operand, fp64 precision
+constexpr int NSG = 6;                        // slices used by the gradient-only contractions of the mixed mode
 constexpr int NS32 = 4;                       // slices per operand, fp32-class precision
 constexpr int SBITS = 8;                      // bits per slice
 constexpr int EOFF = 3;                       // exponent offset: |x| 2^-e < 1/4, so the leading digit fits a signed byte
@@ -59,7 +60,7 @@ template <int NS>
 struct Cfg {
     static constexpr int A_STAGE = NS * OBM * OBK;
     static constexpr int B_STAGE = NS * OBN * OBK;
-    static constexpr int STAGES = (NS > 4) ? 2 : 4;     // 2 x 84 KB (NS = 7) or 4 x 48 KB (NS = 4)
+    static constexpr int STAGES = (NS == 7) ? 2 : (NS == 6) ? 3 : 4;     // 2 x 84 KB (NS = 7), 3 x 72 KB (NS = 6) or 4 x 48 KB (NS = 4)
     static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) + 1024 /*alignment slack*/ + 256 /*barriers*/;
     static constexpr int PRODUCTS = NS * (NS + 1) / 2;
 };
@@ -73,7 +74,7 @@ struct Cfg {
 // rate).  NS = 4: one rounding to 32 bits.
 template <int NS>
 __device__ __forceinline__ void slice_bytes(double t, uint32_t& lo, uint32_t& hi) {
-    static_assert(NS == 7 || NS == 4, "slice_bytes: 7 or 4 slices");
+    static_assert(NS == 7 || NS == 6 || NS == 4, "slice_bytes: operands are sliced with 7 or 4 slices (a 6-slice contraction reads the top six planes of 7)");
     if (NS == 7) {
         const double v1 = t * 268435456.0;                 // 2^28, exact
         const double s1 = v1 + RMAGIC;                     // round-to-nearest-even to an integer: |v1| < 2^31, ulp(1.5 2^52) = 1
@@ -687,6 +688,9 @@ inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, O
 inline cudaError_t launch_ozaki_gemm(int ns, const OzOperand& A, const OzOperand& B, const OzArgs& g, cudaStream_t st) {
     const bool pair = ZIGP_OZ_CL >= 2 && (g.cols / OBN) % 2 == 0;
     if (ns == NS64) return pair ? launch_ozaki_gemm_t<NS64, 2>(A, B, g, st) : launch_ozaki_gemm_t<NS64, 1>(A, B, g, st);
+    // six slices: the top six planes of operands sliced with seven (21 slice products, three pipeline stages) -- gradient-side contractions of
+    // the mixed mode (zigp_set_precision(ctx, 2)); no fused re-slicing in this instance
+    if (ns == NSG && !g.sl_bound2) return pair ? launch_ozaki_gemm_t<NSG, 2>(A, B, g, st) : launch_ozaki_gemm_t<NSG, 1>(A, B, g, st);
     if (ns == NS32) return pair ? launch_ozaki_gemm_t<NS32, 2>(A, B, g, st) : launch_ozaki_gemm_t<NS32, 1>(A, B, g, st);
     return cudaErrorInvalidValue;
 }

@@ -108,6 +108,7 @@ struct zigp_ctx {
     int engine = 0;
     bool oz_ready = false;
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
+    int oz_ns_grad = 0;            // mixed mode: slices used by the gradient-only contractions (Y = G A, rank update); 0 = oz_ns
     int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
     // second stream for latent g (the int8 contractions of one latent overlap the fp64 / memory-bound kernels of the other)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -361,7 +362,7 @@ int oz_product(zigp_ctx* c, Latent& L, int wi, bool from_A, int rows, int tri, d
         if (reslice > 1) { a.sl_cols = L.oz_colA; a.sl_cscale = L.oz_csA; }
     }
     ProfScope ps(c, PC_GEMM, st);
-    CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, a, st));
+    CK(oz::launch_ozaki_gemm((wi == 2 && c->oz_ns_grad && c->oz_ns == oz::NS64) ? c->oz_ns_grad : c->oz_ns, A, B, a, st));   // wi == 2: Y = G A feeds gradients only
     c->launches++;
     return 0;
 }
@@ -467,7 +468,7 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
         a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
         a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
         ProfScope ps(c, PC_SYRK, st);
-        CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, a, st));
+        CK(oz::launch_ozaki_gemm((c->oz_ns_grad && c->oz_ns == oz::NS64) ? c->oz_ns_grad : c->oz_ns, A, B, a, st));
         c->launches++;
         return 0;
     }
@@ -937,7 +938,7 @@ int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if (c->graph_on && !c->profiling && c->has_data) {
         CK(cudaSetDevice(c->device));
-        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns};
+        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad};
         if (!c->gexec || memcmp(&key, &c->gkey, sizeof key) != 0) {
             // (re)capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
             if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
@@ -1142,9 +1143,10 @@ int zigp_int8_config(const zigp_ctx* c, int* slices, int* slice_bits, int* slice
 }
 
 int zigp_set_precision(zigp_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 1) return ZIGP_EINVAL;
-    if (mode == 1 && c->engine != 1) { c->err = "zigp_set_precision: the reduced-precision mode runs on the int8 engine (zigp_set_engine(ctx, 1) first)"; return ZIGP_ESTATE; }
+    if (!c || mode < 0 || mode > 2) return ZIGP_EINVAL;
+    if (mode != 0 && c->engine != 1) { c->err = "zigp_set_precision: the reduced-precision mode runs on the int8 engine (zigp_set_engine(ctx, 1) first)"; return ZIGP_ESTATE; }
     c->oz_ns = mode == 1 ? oz::NS32 : oz::NS64;
+    c->oz_ns_grad = mode == 2 ? oz::NSG : 0;
     return ZIGP_OK;
 }
 

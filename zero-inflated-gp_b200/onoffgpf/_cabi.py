@@ -137,10 +137,11 @@ class Context:
     PROFILE_CLASSES = ("kgen", "gemm_tn", "point", "kgrad", "syrk", "mstage_fwd", "mstage_bwd", "reduce", "slice")
 
     ENGINES = {"dmma": 0, "int8": 1}
-    PRECISIONS = {"fp64": 0, "fp32": 1}
+    PRECISIONS = {"fp64": 0, "fp32": 1, "fp64-grad6": 2}
 
     def set_precision(self, precision):
-        """'fp64' (7 x 8-bit slices) or 'fp32' (4 x 8-bit slices: reduced precision, rel 1e-4 class) -- int8 engine only"""
+        """'fp64' (7 x 8-bit slices), 'fp32' (4 x 8-bit slices: reduced precision, rel 1e-4 class) or 'fp64-grad6' (ELBO path 7 slices,
+        gradient-only contractions 6: same ELBO, ~10 x the float64 gradient error) -- int8 engine only"""
         self.call("zigp_set_precision", self.PRECISIONS[precision] if isinstance(precision, str) else int(precision))
 
     def set_graph(self, on: bool):
