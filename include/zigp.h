@@ -50,7 +50,7 @@ typedef struct zigp_ctx zigp_ctx;
 
 /* Create a context on GPU `device` for Mf / Mg inducing points and D input dimensions (D <= ZIGP_MAX_D).
  * jitter: added to diag(Kmm) (gpflow settings.numerics.jitter_level = 1e-6 at onoffgpf/OnOffSVGP.py:96-97).
- * chunk_rows: points processed per pass of the N-stage pipeline (0 = default). */
+ * chunk_rows: points processed per pass of the N-stage pipeline (0 = default, 65536). */
 int zigp_create(zigp_ctx** ctx, int device, int Mf, int Mg, int D, double jitter, int64_t chunk_rows);
 /* The same with the model branch chosen (onoffgpf/OnOffSVGP.py:33-34, :64-71, :88-104; gpflow conditional / gauss_kl* = onofftf/main.py:187-305):
  * whiten = 1: whitened representation (mean = A^T q_mu, KL of gauss_kl_white*); q_full = 1: full lower-triangular q_sqrt -- theta then
@@ -109,14 +109,19 @@ int zigp_prior_kl_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, v
  * (gfmean, gfvar, gfmeanu, fmean, fvar, gmean, gvar, ephi_g, evar_phi_g). */
 int zigp_predict_dev(zigp_ctx* ctx, const double* theta_dev, const double* Xnew_dev, int64_t n_new, double* out9_dev, void* stream);
 int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xnew_host, int64_t n_new, double* out9_host, void* stream);
+/* Cholesky status of the last prior_kl / predict / elbo_grad call issued on `stream` (synchronises the stream): *info = 0, or k > 0 as in
+ * out[3].  The reference raises a TF InvalidArgumentError from tf.cholesky (onofftf/main.py:200,268); device-pointer predict calls cannot
+ * return it, so bindings read it here (zigp_predict_host does, and returns ZIGP_ENOTPD). */
+int zigp_read_info(zigp_ctx* ctx, int64_t* info, void* stream);
 
 /* Test / profiling hooks: view of an internal device buffer after the last call.
  * name: "L","T","Kmm","alpha_w","beta","E","a","G","K","A","RA","V","Y","mean","var","gm","gv" ; latent 0 = f, 1 = g. */
 int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
-/* Contraction engine of the dense path: 0 = DMMA (fp64 mma.sync, the default), 1 = fp64 emulated exactly-sliced on the INT8 tensor
+/* Contraction engine of the dense path: 0 = DMMA (fp64 mma.sync), 1 = fp64 emulated exactly-sliced on the INT8 tensor
  * cores (tcgen05.mma kind::i8; csrc/ozaki.cuh: 7 x 8-bit slices per operand, int32 accumulation in TMEM, fp64 recombination --
  * same worst-case error bound as an fp64 dot product, ~2-3x the DMMA rate).  Allocates the slice workspaces on first use.
- * zigp_create selects engine 1 unless the environment says ZIGP_ENGINE=dmma. */
+ * Engine 1 is the default: zigp_create selects it unless the environment says ZIGP_ENGINE=dmma, and FAILS (no silent downgrade) if it
+ * cannot be set up. */
 int zigp_set_engine(zigp_ctx* ctx, int engine);
 int zigp_get_engine(const zigp_ctx* ctx);
 /* configuration of the int8 engine of this context: slices per operand, bits per slice, int8 slice products per product (NS (NS+1) / 2) */
@@ -133,6 +138,10 @@ int zigp_set_precision(zigp_ctx* ctx, int mode);
  * cores, csrc/ozaki.cuh), so that the two engines can be compared on the same operands. */
 int zigp_debug_gemm(zigp_ctx* ctx, int engine, const double* In_dev, int64_t ldi, const double* W_dev, int64_t ldw, double* Out_dev, int64_t ldo,
                     int rows, int cols, int kdim, int tri, double* stat_sq_dev, void* stream);
+/* Measurement hook: launches the int8 tensor-pipe issue loop (csrc/ozaki.cuh: i8_peak_kernel -- every SM issues 2 * iters tcgen05.mma kind::i8
+ * of shape 128 x n x 32 on shared-memory-resident operands, no loads, no epilogue) on `stream` and returns the integer operations of that
+ * launch.  The caller times it with CUDA events; bench.py uses the result as the measured int8 peak of `roofline`.  No reference counterpart. */
+int zigp_debug_int8_peak(zigp_ctx* ctx, int iters, int n, double* ops_per_launch, void* stream);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t zigp_launch_count(const zigp_ctx* ctx);
 /* Per-kernel-class device timing (CUDA events recorded on the launching stream around each launch).  Classes:

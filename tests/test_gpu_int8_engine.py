@@ -64,10 +64,11 @@ def test_engines_agree_at_scale():
         assert np.linalg.norm(ga[k] - gb[k]) <= 1e-10 * np.linalg.norm(gb[k]) + 1e-13 * full, k
 
 
-@pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small"])
+@pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small", "cfg2_M512", "cfg3_M1024"])
 def test_reduced_precision_mode_within_1e_4(name):
     """BASELINE.json's fp32 mode (configs[2]: "fp32 and fp64"): contractions with 4 x 8-bit slices (31 bits below each row's scale),
-    everything else fp64; tolerance rel 1e-4 on the ELBO and on every gradient block (norm-wise), against the float64 oracle goldens"""
+    everything else fp64; tolerance rel 1e-4 on the ELBO and on every gradient block (norm-wise), against the float64 goldens produced by the reference's own source
+    (cfg2_M512 is BASELINE.json configs[2] -- "fp32 and fp64" -- at its own M = 512, D = 2)"""
     import os
     from oracle import onoff_oracle as orc
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_%s.npz" % name))
@@ -88,7 +89,31 @@ def test_reduced_precision_mode_within_1e_4(name):
         err = np.linalg.norm(a - b)
         assert err <= 1e-4 * np.linalg.norm(b) + 1e-7 * full, (k, err / np.linalg.norm(b))
         worst = max(worst, err / (np.linalg.norm(b) + 1e-300))
+    assert abs(out[0] - float(z["elbo"])) > 0          # it IS the reduced mode
     print("fp32-class mode, %s: ELBO rel err %.2e, worst gradient block rel err %.2e" % (name, abs(out[0] - float(z["elbo"])) / abs(float(z["elbo"])), worst))
+
+
+def test_reduced_precision_mode_where_the_1e_4_claim_ends():
+    """a 31-bit operand representation cannot hold 1e-4 once cond(Kmm) approaches 1e6-1e7.  On the ill-conditioned fixture
+    (cond 4.6e6 / 7.9e6) the ELBO still meets 1e-4 but the gradient does not have to: the test states the measured class (<= 5e-2 norm-wise)
+    so that a regression OR a silent widening of the claim shows up; the fp64 mode on the same fixture is test_golden_ill_conditioned."""
+    import os
+    from oracle import onoff_oracle as orc
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_illcond.npz"))
+    N, Mf, Mg, D, seed, nd = (int(z[k]) for k in ("N", "Mf", "Mg", "D", "seed", "num_data"))
+    X, Y = synth.make_data(N, D, seed)
+    p = {k: z["p_" + k] for k in orc.PARAM_NAMES}
+    m = synth.build_model(X, Y, p, engine="int8", precision="fp32")
+    m.num_data = nd
+    m.build_likelihood()
+    out = m._last_out.cpu().numpy()
+    assert out[3] == 0 and np.all(np.isfinite(out))
+    e_err = abs(out[0] - float(z["elbo"])) / abs(float(z["elbo"]))
+    gref = np.concatenate([z["g_" + k].reshape(-1) for k in orc.PARAM_NAMES])
+    g = synth.unpack_grad(out[4:], Mf, Mg, D)
+    gerr = np.linalg.norm(np.concatenate([np.asarray(g[k]).reshape(-1) for k in orc.PARAM_NAMES]) - gref) / np.linalg.norm(gref)
+    print("fp32-class mode at cond ~6e6: ELBO rel err %.2e, gradient rel err %.2e" % (e_err, gerr))
+    assert e_err <= 1e-4 and gerr <= 5e-2
 
 
 def test_rank_update_split_guard_on_a_short_last_chunk():

@@ -6,8 +6,10 @@ of this objective differ by ~eps*cond(Kmm) per gradient entry (the
 forms differ by 7e-10 on the toy config), so the tests use:
   * ELBO, data term, KL:            rel 1e-10
   * each gradient block, norm-wise: rel 1e-9 (+ 1e-12 of the full gradient norm, for blocks that are pure cancellation) on well-conditioned synthetic configs (cond(Kmm) <~ 1e5; measured ~1e-12),
-                                    rel 1e-6 on the badly conditioned toy initialisation (cond 1.6e5 with lengthscale 2 on a
-                                    unit grid), where the mpmath referee test below shows which side is closer to the truth.
+                                    rel 5e-9 on the badly conditioned toy initialisation (cond 1.6e5 with lengthscale 2 on a unit grid:
+                                    the reference's own free-state round trip moves its gradient by 4e-10 there, fixture key oracle_dev),
+                                    and 1e-10 against the 50-digit referee on the same configuration (toy_referee.npz).
+Golden values are the reference's own (unmodified source through oracle/refshim, tests/golden/make_golden.py).
 """
 import os
 
@@ -64,9 +66,12 @@ def engine(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small", "ragged"])
+# Golden values are the REFERENCE's (its unmodified source run through oracle/refshim; tests/golden/make_golden.py).  cfg2_M512 / cfg3_M1024
+# are BASELINE.json configs[2] / [3] at their own M and D (a 16384-point batch of N = 2^20 / 2^24, with the minibatch scale).
+@pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small", "ragged", "cfg2_M512", "cfg3_M1024"])
 def test_golden_synthetic(name):
     z = np.load(os.path.join(G, "synth_%s.npz" % name))
+    assert str(z["source"]) == "reference-via-shim"
     N, Mf, Mg, D, seed, nd = (int(z[k]) for k in ("N", "Mf", "Mg", "D", "seed", "num_data"))
     X, Y = synth.make_data(N, D, seed)
     p = {k: z["p_" + k] for k in orc.PARAM_NAMES}
@@ -78,6 +83,25 @@ def test_golden_synthetic(name):
     assert m.compute_prior_KL() == pytest.approx(float(z["kl"]), rel=1e-10)
 
 
+def test_golden_ill_conditioned():
+    """lengthscale = 1.5 x the inducing-grid spacing: cond(Kmm + 1e-6 I) = 4.6e6 / 7.9e6.  Two float64 evaluations of the objective differ by
+    ~cond x 1e-16 here (the reference-via-shim and the CPU oracle by 6e-11 on the gradient, fixture key oracle_dev); the CUDA path is held to
+    the 1e-10 class on the ELBO parts and to 2e-9 on every gradient block -- the tolerance it meets, stated (profiles/cond_study_r01.txt)."""
+    z = np.load(os.path.join(G, "synth_illcond.npz"))
+    N, Mf, Mg, D, seed, nd = (int(z[k]) for k in ("N", "Mf", "Mg", "D", "seed", "num_data"))
+    assert float(z["cond_f"]) > 1e6 and float(z["cond_g"]) > 1e6
+    X, Y = synth.make_data(N, D, seed)
+    p = {k: z["p_" + k] for k in orc.PARAM_NAMES}
+    m, out, gc, gf = evaluate(X, Y, p, num_data=nd)
+    assert out[3] == 0
+    e, dt, kl = float(z["elbo"]), float(z["data"]), float(z["kl"])
+    assert abs(out[0] - e) <= 5e-10 * abs(e) and abs(out[1] - dt) <= 5e-10 * abs(dt) and abs(out[2] - kl) <= 5e-10 * abs(kl)
+    full = np.sqrt(sum(float(np.sum(np.square(z["g_" + k]))) for k in orc.PARAM_NAMES))
+    for k in orc.PARAM_NAMES:
+        a, b = np.asarray(gc[k]).reshape(-1), z["g_" + k].reshape(-1)
+        assert np.linalg.norm(a - b) <= 2e-9 * np.linalg.norm(b) + 1e-12 * full, (k, relnorm(a, b))
+
+
 @pytest.mark.parametrize("suffix", ["a_", "b_"])
 def test_golden_toy_reference_data(suffix):
     """configs[0]: the reference's toy data set with the notebook's initialisation (zero-inflated-gpflow.ipynb:94-135)"""
@@ -85,8 +109,25 @@ def test_golden_toy_reference_data(suffix):
     p = {k: z[suffix + "p_" + k] for k in orc.PARAM_NAMES}
     m, out, gc, gf = evaluate(z["x"], z["y"], p)
     check_against(out, gc, gf, float(z[suffix + "elbo"]), float(z[suffix + "data"]), float(z[suffix + "kl"]),
-                  {k: z[suffix + "g_" + k] for k in orc.PARAM_NAMES}, {k: z[suffix + "gf_" + k] for k in orc.PARAM_NAMES}, 1e-6)
+                  {k: z[suffix + "g_" + k] for k in orc.PARAM_NAMES}, {k: z[suffix + "gf_" + k] for k in orc.PARAM_NAMES}, 5e-9)
     np.testing.assert_allclose(np.concatenate(m.predict_onoffgp(z["x"][:64]), 1), z[suffix + "pred"], rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("suffix", ["a_", "b_"])
+def test_toy_conditioning_against_the_50_digit_referee(suffix):
+    """Who is right at cond(Kmm) = 1.6e5?  tests/golden/toy_referee.npz holds 50-digit values (oracle/mp_oracle.py) on every 10th row of the
+    reference's toy data at the notebook's initialisation.  The float64 evaluations of the reference itself sit 1.6e-12 (ELBO) and up to 3e-11
+    (gradient blocks; the near-cancelling scalar kernf_variance 7e-10) from those values; the CUDA path is held to the same class:
+    ELBO 1e-11, every gradient block 1e-10 norm-wise (+ 1e-12 of the whole gradient for the cancelling scalar)."""
+    z = np.load(os.path.join(G, "toy_referee.npz"))
+    p = {k: z[suffix + "p_" + k] for k in orc.PARAM_NAMES}
+    m, out, gc, _ = evaluate(z["x"], z["y"], p, num_data=int(z["num_data"]))
+    e0 = float(z[suffix + "elbo"])
+    assert abs(out[0] - e0) <= 1e-11 * abs(e0), abs(out[0] - e0) / abs(e0)
+    full = np.sqrt(sum(float(np.sum(np.square(z[suffix + "g_" + k]))) for k in orc.PARAM_NAMES))
+    for k in orc.PARAM_NAMES:
+        a, b = np.asarray(gc[k]).reshape(-1), z[suffix + "g_" + k].reshape(-1)
+        assert np.linalg.norm(a - b) <= 1e-10 * np.linalg.norm(b) + 1e-12 * full, (k, relnorm(a, b))
 
 
 def test_mpmath_referee_tiny():
@@ -181,9 +222,12 @@ def test_host_pointer_entry_points_match_device_entry_points():
 
 
 def test_reference_api_surface_and_training_reaches_notebook_band():
-    """the notebook flow (zero-inflated-gpflow.ipynb:94-156) with the reference's names; L-BFGS-B from a seeded init must land
-    in the band of the published optimum (488.71; SURVEY.md: 485.5 from another seed)"""
+    """the notebook flow (zero-inflated-gpflow.ipynb cells 5-7) with the reference's names: ``m.optimize(maxiter=8000)`` = L-BFGS-B on the free
+    state from the same seeded initialisation as tests/golden/make_toy_training.py, where the REFERENCE's own class (through oracle/refshim)
+    ends at 480.61 after its 8000 iterations (fixture toy_training.npz; the notebook's unseeded run printed 488.713, the survey's 485.51).
+    L-BFGS paths separate after a few hundred iterations (rounding), so the end point is held to the band those three runs span, not to a value."""
     z = np.load(os.path.join(G, "toy.npz"))
+    t = np.load(os.path.join(G, "toy_training.npz"))
     X, Y = z["x"], z["y"]
     kf = RBF(1); kf.lengthscales = 2.0; kf.variance = 1.0
     kg = RBF(1); kg.lengthscales = 2.0; kg.variance = 5.0
@@ -193,14 +237,34 @@ def test_reference_api_surface_and_training_reaches_notebook_band():
     m.likelihood.variance = 0.01
     m.likelihood.variance.fixed = False
     e0 = m.compute_log_likelihood()
-    m.optimize(maxiter=3000)
+    assert e0 == pytest.approx(float(t["elbo_init"]), rel=1e-10)         # same start as the reference's recorded run
+    res = m.optimize(maxiter=8000)
     e1 = m.compute_log_likelihood()
-    assert e1 > e0 and 430.0 < e1 < 520.0, (e0, e1)
+    print("L-BFGS-B %d iterations: ELBO %.3f -> %.3f (reference class from the same start: %.3f; notebook: 488.713)" % (res.nit, e0, e1, float(t["elbo_opt"])))
+    assert 478.0 <= e1 <= 492.0, (e0, e1)
     out = m.predict_onoffgp(X)
     assert len(out) == 9 and all(o.shape == (450, 1) for o in out)
     for attr in ("Xtrain", "Ytrain", "Zf", "Zg", "u_fm", "u_gm", "u_fs_sqrt", "u_gs_sqrt"):
         assert getattr(m, attr).value.shape[0] > 0
     assert m.kernf.compute_K_symm(X).shape == (450, 450) and m.likelihood.variance.value.shape == (1,)
+
+
+def test_parity_at_the_reference_optimised_parameters():
+    """the other end of the training run: ELBO, KL, gradient and predictions at the parameters the REFERENCE's class reached after its 8000
+    L-BFGS-B iterations (toy_training.npz) -- a fitted model (q_sqrt ~ 0.01, noise 0.004, var_g 178) instead of an initialisation"""
+    z = np.load(os.path.join(G, "toy.npz"))
+    t = np.load(os.path.join(G, "toy_training.npz"))
+    assert str(t["source"]) == "reference-via-shim"
+    p = {k: t["p_" + k] for k in orc.PARAM_NAMES}
+    m, out, gc, _ = evaluate(z["x"], z["y"], p)
+    assert out[3] == 0
+    assert abs(out[0] - float(t["elbo"])) <= 1e-10 * abs(float(t["data"])) and abs(out[2] - float(t["kl"])) <= 1e-10 * abs(float(t["kl"]))
+    assert abs(out[1] - float(t["data"])) <= 1e-10 * abs(float(t["data"]))
+    full = np.sqrt(sum(float(np.sum(np.square(t["g_" + k]))) for k in orc.PARAM_NAMES))
+    for k in orc.PARAM_NAMES:
+        a, b = np.asarray(gc[k]).reshape(-1), t["g_" + k].reshape(-1)
+        assert np.linalg.norm(a - b) <= 1e-8 * np.linalg.norm(b) + 1e-10 * full, (k, relnorm(a, b))
+    np.testing.assert_allclose(np.concatenate(m.predict_onoffgp(z["x"][:64]), 1), t["pred"], rtol=1e-8, atol=1e-10)
 
 
 def test_size_independent_properties_at_scale():

@@ -28,6 +28,7 @@ def golden_case(name):
 @pytest.mark.parametrize("name", ["kron_small", "kron_pptr"])
 def test_oracle_reproduces_golden_and_structured_model_agrees(name):
     d, X, Y, p = golden_case(name)
+    assert str(d["source"]) == "reference-via-shim"      # values of the reference's own scripts/onoff.py functions (tests/golden/make_golden.py)
     q = kro.as_params(**p)
     n = 400 if name == "kron_pptr" else None          # the dense-kron oracle is O(M^2 N): bound the CPU suite
     if n is None:

@@ -1,5 +1,7 @@
-"""The oracle against (1) the SURVEY.md 8(c) known answers on the reference's toy data, (2) the committed golden vectors,
-(3) a 50-digit mpmath referee, (4) finite differences, and (5) the CPU model of the device algorithm (tests/algo_model.py)."""
+"""The oracle against (1) the SURVEY.md 8(c) known answers on the reference's toy data, (2) the committed golden vectors -- which hold the
+values the REFERENCE's own source produces (unmodified onoffgpf/OnOffSVGP.py etc. run through oracle/refshim; tests/golden/make_golden.py;
+tests/test_reference_shim.py re-runs the reference live where /root/reference exists), (3) a 50-digit mpmath referee, (4) finite
+differences, and (5) the CPU model of the device algorithm (tests/algo_model.py)."""
 import os
 
 import numpy as np
@@ -37,19 +39,62 @@ def test_survey_known_answers_toy():
     assert kl == pytest.approx(2.381018897065870e+04, rel=1e-12)
 
 
-@pytest.mark.parametrize("name", ["cfg3_small", "cfg4_small", "ragged"])
-def test_oracle_reproduces_golden(name):
+def _relnorm(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1); b = np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+@pytest.mark.parametrize("name,gtol", [("cfg3_small", 1e-10), ("cfg4_small", 1e-10), ("ragged", 1e-10), ("cfg2_M512", 1e-10), ("cfg3_M1024", 1e-10),
+                                       ("illcond", 1e-9)])
+def test_oracle_equals_the_reference_values(name, gtol):
+    """the pin of SURVEY 8(c): the fixture values come from the reference's own source (source tag), and the restatement reproduces them --
+    ELBO / data term / KL to 1e-12, every gradient block (constrained and free space) norm-wise to 1e-10 (1e-9 at cond 6e6), the nine
+    prediction outputs to 1e-11"""
     z = np.load(os.path.join(G, "synth_%s.npz" % name))
+    assert str(z["source"]) == "reference-via-shim"
     N, Mf, Mg, D, seed = (int(z[k]) for k in ("N", "Mf", "Mg", "D", "seed"))
     X, Y = synth.make_data(N, D, seed)
     p = orc.as_params(**{k: z["p_" + k] for k in orc.PARAM_NAMES})
     e, dt, kl, g = orc.elbo_and_grads(X, Y, p, num_data=int(z["num_data"]))
-    assert e == pytest.approx(float(z["elbo"]), rel=1e-11)
-    assert kl == pytest.approx(float(z["kl"]), rel=1e-11)
+    _, _, _, gf = orc.elbo_and_grads(X, Y, p, num_data=int(z["num_data"]), free=True)
+    assert e == pytest.approx(float(z["elbo"]), rel=1e-12)
+    assert kl == pytest.approx(float(z["kl"]), rel=1e-12)
+    assert dt == pytest.approx(float(z["data"]), rel=1e-12)
     for k in orc.PARAM_NAMES:
-        np.testing.assert_allclose(g[k].numpy(), z["g_" + k], rtol=1e-7, atol=1e-9 * np.abs(z["g_" + k]).max())
+        assert _relnorm(g[k].numpy(), z["g_" + k]) <= gtol, k
+        assert _relnorm(gf[k].numpy(), z["gf_" + k]) <= gtol, "free " + k
     pred = np.concatenate(orc.predict_onoffgp(X[:64], p), 1)
-    np.testing.assert_allclose(pred, z["pred"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(pred, z["pred"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("sfx", ["a_", "b_"])
+def test_oracle_equals_the_reference_values_on_the_toy_data(sfx):
+    """configs[0]: cond(Kmm) = 1.6e5, so a one-ulp re-rounding of the parameters (the reference keeps free states) moves gradient entries by
+    ~4e-10 (fixture key oracle_dev); the blocks are held to 1e-9"""
+    z = np.load(os.path.join(G, "toy.npz"))
+    assert str(z[sfx + "source"]) == "reference-via-shim" and float(z[sfx + "oracle_dev"]) < 1e-9
+    p = toy_params(z, sfx)
+    e, dt, kl, g = orc.elbo_and_grads(z["x"], z["y"], p)
+    _, _, _, gf = orc.elbo_and_grads(z["x"], z["y"], p, free=True)
+    assert e == pytest.approx(float(z[sfx + "elbo"]), rel=1e-13) and kl == pytest.approx(float(z[sfx + "kl"]), rel=1e-13)
+    for k in orc.PARAM_NAMES:
+        assert _relnorm(g[k].numpy(), z[sfx + "g_" + k]) <= 1e-9, k
+        assert _relnorm(gf[k].numpy(), z[sfx + "gf_" + k]) <= 1e-9, "free " + k
+
+
+@pytest.mark.parametrize("sfx", ["a_", "b_"])
+def test_oracle_against_the_50_digit_referee_at_the_toy_conditioning(sfx):
+    """cond(Kmm) = 1.6e5 (tests/golden/toy_referee.npz, every 10th toy row): how far a float64 evaluation of the reference's formulas sits from
+    the exact value -- ELBO 2e-12, gradient blocks <= 5e-11 except the cancelling scalar kernf_variance; the GPU test holds the CUDA path to the
+    same class"""
+    z = np.load(os.path.join(G, "toy_referee.npz"))
+    p = orc.as_params(**{k: z[sfx + "p_" + k] for k in orc.PARAM_NAMES})
+    e, _, _, g = orc.elbo_and_grads(z["x"], z["y"], p, num_data=int(z["num_data"]))
+    assert abs(e - float(z[sfx + "elbo"])) <= 1e-11 * abs(e)
+    full = np.sqrt(sum(float(np.sum(np.square(z[sfx + "g_" + k]))) for k in orc.PARAM_NAMES))
+    for k in orc.PARAM_NAMES:
+        a, b = g[k].numpy().reshape(-1), z[sfx + "g_" + k].reshape(-1)
+        assert np.linalg.norm(a - b) <= 1e-10 * np.linalg.norm(b) + 1e-12 * full, k
 
 
 def _flat(g):

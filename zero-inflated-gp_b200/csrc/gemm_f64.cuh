@@ -22,6 +22,7 @@ namespace zigp {
 #ifndef ZIGP_RASTER
 #define ZIGP_RASTER 0
 #endif
+constexpr int MAX_DEVICES = 64;   // per-device launch state (function attributes, SM counts) is kept for this many GPUs per process
 constexpr int KT = ZIGP_KT;     // k-slab depth (doubles) staged per pipeline stage
 constexpr int SPAD = 4;         // row padding -> stride 20 doubles == 4 (mod 16): DMMA fragment loads hit 32 distinct banks
 constexpr int SSTR = KT + SPAD;
@@ -250,11 +251,14 @@ template <int BM, int BN, int WM, int WN, int STAGES, int MINB = 1>
 inline cudaError_t launch_gemm_tn(const GemmArgs& g, cudaStream_t st) {
     using C = TnCfg<BM, BN, WM, WN, STAGES, MINB>;
     auto kern = gemm_tn_f64<BM, BN, WM, WN, STAGES, MINB>;
-    static bool attr_done = false;   // per-instantiation; contexts are created per device before first use
-    if (!attr_done) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of the function: remember it per device, per instantiation
+    static bool attr_done[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MAX_DEVICES || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < MAX_DEVICES) attr_done[dev] = true;
     }
     if (g.rows <= 0 || g.cols <= 0) return cudaSuccess;
     dim3 grid((g.rows / BM) * (g.cols / BN));
@@ -381,11 +385,13 @@ template <int BT, int WM, int WN, int STAGES, int MINB = 1, bool FULL = false>
 inline cudaError_t launch_syrk_nt(const SyrkArgs& g, cudaStream_t st) {
     using C = NtCfg<BT, WM, WN, STAGES, MINB>;
     auto kern = syrk_nt_f64<BT, WM, WN, STAGES, MINB, FULL>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MAX_DEVICES || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < MAX_DEVICES) attr_done[dev] = true;
     }
     int nt = g.m / BT;
     dim3 grid(FULL ? nt * (g.mj / BT) : nt * (nt + 1) / 2, g.nsplit);

@@ -139,7 +139,7 @@ int kron_chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, i
 
 int kron_accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     if (!c->has_data) { c->err = "zigp: no data set (call zigp_set_data_* first)"; return ZIGP_ESTATE; }
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     CK(cudaMemsetAsync(c->pt_partial, 0, (size_t)c->pt_slots * 4 * sizeof(double), st));
     for (int l = 0; l < c->nlat; l++) {
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) kron_finalize_kernel(const KronFinalArgs 
 }
 
 int kron_finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     ProfScope ps(c, PC_MBWD, st);
     KronFinalArgs f{};
     f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.off_noise = c->off_noise; f.nlat = c->nlat;
@@ -282,7 +282,7 @@ int kron_finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) 
 }
 
 int kron_prior_kl(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     for (int l = 0; l < c->nlat; l++) RUN(kron_mstage_forward(c, l, theta, st));
     kl_out_kernel<<<1, 1, 0, st>>>(c->klat[0].kl, c->nlat > 1 ? c->klat[1].kl : c->zero2, c->info, out);
@@ -291,7 +291,7 @@ int kron_prior_kl(zigp_ctx* c, const double* theta, double* out, cudaStream_t st
 }
 
 int kron_predict(zigp_ctx* c, const double* theta, const double* Xnew, long long n_new, double* out9, cudaStream_t st) {
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     for (int l = 0; l < c->nlat; l++) RUN(kron_mstage_forward(c, l, theta, st));
     for (long long n0 = 0; n0 < n_new; n0 += c->chunk) {

@@ -616,6 +616,61 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
     }
 }
 
+// ---- int8 tensor-pipe peak (measurement hook) ----------------------------------------------------------------------------------
+// The ceiling the contraction kernel is measured against: one thread per SM issues `iters` x 2 tcgen05.mma kind::i8 of shape 128 x N x 32
+// back to back on operands that already sit in shared memory (no TMA, no epilogue; pseudo-random bytes so that the data path toggles as
+// in the real kernel), alternating between two TMEM accumulator tiles.  N = 256 needs 96 B/clk of the 128 B/clk shared-memory port, so the
+// loop is bound by the tensor pipe itself: 128 N 32 MACs per instruction in N / 2 cycles = 8192 MAC/clk/SM.  bench.py times it with
+// CUDA events (burst and sustained) and uses the result as `roofline.peak` (MEASURED_PEAKS.json has no int8 entry).
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int N) {
+    extern __shared__ uint8_t pk_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pk_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                        // 128 rows x 64 B
+    uint8_t* sB = smem + 128 * 64;             // 256 rows x 64 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (128 + 256) * 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    for (int i = threadIdx.x; i < (128 + 256) * 64 / 4; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        reinterpret_cast<uint32_t*>(smem)[i] = h;
+    }
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        if (threadIdx.x == 0) { tc05::mbar_init(bar, 1); tc05::fence_barrier_init(); }
+        __syncwarp();
+        tc05::tmem_alloc<512>(tmem_slot);
+    }
+    // generic-proxy writes of the operands must be visible to the tensor core's async proxy
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    tc05::fence_before_thread_sync();
+    __syncthreads();
+    tc05::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t a_base = tc05::smem_u32(sA), b_base = tc05::smem_u32(sB);
+        const uint32_t idesc = tc05::idesc_i8(128, N);
+        const uint64_t da0 = tc05::smem_desc_kmajor<64>(a_base), da1 = tc05::smem_desc_kmajor<64>(a_base + 32);
+        const uint64_t db0 = tc05::smem_desc_kmajor<64>(b_base), db1 = tc05::smem_desc_kmajor<64>(b_base + 32);
+        for (int i = 0; i < iters; i++) {
+            tc05::mma_i8(tmem_base, da0, db0, idesc, i ? 1u : 0u);
+            tc05::mma_i8(tmem_base + 256u, da1, db1, idesc, i ? 1u : 0u);
+        }
+        tc05::mma_commit(bar);
+        tc05::mbar_wait(bar, 0);
+        tc05::fence_after_thread_sync();
+    }
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc<512>(tmem_base);
+}
+
+inline cudaError_t launch_i8_peak(int iters, int N, int n_sms, double* ops, cudaStream_t st) {
+    if (iters <= 0 || N < 16 || N > 256 || N % 16) return cudaErrorInvalidValue;
+    const int smem = (128 + 256) * 64 + 1024 + 64;
+    i8_peak_kernel<<<n_sms, 128, smem, st>>>(iters, N);
+    if (ops) *ops = 2.0 /*op per MAC*/ * 2.0 /*MMAs per iteration*/ * (double)iters * 128.0 * N * 32.0 * n_sms;
+    return cudaGetLastError();
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -651,15 +706,18 @@ struct OzOperand {                   // a sliced matrix: ns planes of nrows x K 
 template <int NS, int CL>
 inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
     auto kern = ozaki_gemm_kernel<NS, CL>;
-    static bool attr_done = false;
-    static int n_sms = 0;
-    if (!attr_done) {
+    // per-device opt-in to the dynamic shared memory size and per-device SM count (one process may hold contexts on several GPUs)
+    static int sms_of[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool slot = dev >= 0 && dev < MAX_DEVICES;
+    int n_sms = slot ? sms_of[dev] : 0;
+    if (n_sms == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NS>::SMEM);
         if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_done = true;
+        e = cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (slot) sms_of[dev] = n_sms;
     }
     CUtensorMap ma, ma2, mb;
     constexpr int PL = (NS + CL - 1) / CL, PL2 = NS - PL * (CL - 1);

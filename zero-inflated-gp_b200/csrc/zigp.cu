@@ -88,6 +88,7 @@ struct zigp_ctx {
     // data
     const double* X = nullptr; const double* Y = nullptr;
     double *Xown = nullptr, *Yown = nullptr; long long own_cap = 0;
+    double *pred_x = nullptr, *pred_o = nullptr; long long pred_cap = 0;      // staging of zigp_predict_host, grown on demand and kept
     long long n_local = 0; double scale = 1.0; bool has_data = false;
     // accumulators
     double* accum = nullptr; long long accum_len = 0;
@@ -150,6 +151,19 @@ namespace {
     } while (0)
 
 inline long long rup(long long x, long long a) { return (x + a - 1) / a * a; }
+
+// Every entry point runs on the context's GPU and leaves the caller's current device as it found it (a model built or garbage-collected on
+// cuda:1 must not flip the thread's current device under torch).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 enum ProfCat { PC_KGEN = 0, PC_GEMM = 1, PC_POINT = 2, PC_KGRAD = 3, PC_SYRK = 4, PC_MFWD = 5, PC_MBWD = 6, PC_REDUCE = 7, PC_SLICE = 8, PC_COUNT = 9 };
 
@@ -483,7 +497,7 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
 
 int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     if (!c->has_data) { c->err = "zigp: no data set (call zigp_set_data_* first)"; return ZIGP_ESTATE; }
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     const int D = c->D;
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     CK(cudaMemsetAsync(c->pt_partial, 0, (size_t)c->pt_slots * 4 * sizeof(double), st));
@@ -637,7 +651,7 @@ int finish_generic_latent(zigp_ctx* c, Latent& L, const double* theta, const dou
 }
 
 int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     ProfScope ps(c, PC_MBWD, st);
     const int D = c->D;
     FinalArgs f{};
@@ -725,7 +739,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     zigp_ctx* c = new zigp_ctx();
     c->device = device; c->D = D; c->jitter = jitter; c->whiten = whiten != 0; c->q_full = q_full != 0;
     auto fail = [&](int code) { g_create_error = c->err; zigp_destroy(c); return code; };
-    if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(ZIGP_ECUDA); }
+    DeviceGuard guard(device);
     int cc_major = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
     if (cc_major != 10) { c->err = "libzigp is built for sm_100a (B200) only"; return fail(ZIGP_ECUDA); }
@@ -738,7 +752,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     for (int l = 0; l < 2; l++) { c->lat[l].off_s = off; off += c->q_full ? (long long)Ms[l] * Ms[l] : Ms[l]; }
     c->theta_len = off;
 
-    long long chunk = chunk_rows > 0 ? chunk_rows : 32768;
+    long long chunk = chunk_rows > 0 ? chunk_rows : 65536;     // the tuned value (profiles/tune_r01*.txt); the Python mirror passes the same
     chunk = rup(chunk, 512);
     c->chunk = chunk;
     c->pt_slots = (int)(chunk / 256);
@@ -807,7 +821,11 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     // default engine: fp64 on the int8 tensor cores; ZIGP_ENGINE=dmma (or zigp_set_engine(ctx, 0)) selects the DMMA engine
     if (const char* fz = getenv("ZIGP_OZ_FUSE")) c->oz_fuse = atoi(fz);
     const char* env = getenv("ZIGP_ENGINE");
-    if (!(env && std::string(env) == "dmma") && zigp_set_engine(c, 1) != ZIGP_OK) c->engine = 0;
+    if (!(env && std::string(env) == "dmma")) {
+        // no silent downgrade: a context that cannot set up its default engine fails to create (ZIGP_ENGINE=dmma asks for the DMMA engine)
+        const int r = zigp_set_engine(c, 1);
+        if (r != ZIGP_OK) return fail(r);
+    }
     *out = c;
     return ZIGP_OK;
 }
@@ -837,7 +855,7 @@ int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g
     c->device = device; c->kron = true; c->Ds = Ds; c->Dt = Dt; c->D = Ds + Dt; c->jitter = jitter;
     c->nlat = model == 0 ? 2 : 1; c->lik = model;
     auto fail = [&](int code) { g_create_error = c->err; zigp_destroy(c); return code; };
-    if (cudaSetDevice(device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return fail(ZIGP_ECUDA); }
+    DeviceGuard guard(device);
     int cc_major = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
     if (cc_major != 10) { c->err = "libzigp is built for sm_100a (B200) only"; return fail(ZIGP_ECUDA); }
@@ -855,11 +873,12 @@ int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g
 
 int zigp_destroy(zigp_ctx* c) {
     if (!c) return ZIGP_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
     if (c->Xown) cudaFree(c->Xown);
     if (c->Yown) cudaFree(c->Yown);
+    cudaFree(c->pred_x); cudaFree(c->pred_o);
     cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
     if (c->aux) cudaStreamDestroy(c->aux);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
@@ -891,7 +910,7 @@ int zigp_set_data_dev(zigp_ctx* c, const double* X, const double* Y, int64_t n, 
 int zigp_set_data_host(zigp_ctx* c, const double* X, const double* Y, int64_t n, double scale, void* stream) {
     if (!c) return ZIGP_EINVAL;
     if (!X || !Y || n <= 0 || !(scale > 0.0)) { c->err = "zigp_set_data: bad argument"; return ZIGP_EINVAL; }
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (n > c->own_cap) {
         CK(cudaStreamSynchronize(st));
@@ -926,7 +945,7 @@ int zigp_finish_dev(zigp_ctx* c, const double* theta, double* out, void* stream)
 
 int zigp_set_graph(zigp_ctx* c, int on) {
     if (!c) return ZIGP_EINVAL;
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     if (on && !c->cap) CK(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
     if (!on && c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
     c->graph_on = on != 0;
@@ -937,7 +956,7 @@ int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stre
     if (!c || !theta || !out) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (c->graph_on && !c->profiling && c->has_data) {
-        CK(cudaSetDevice(c->device));
+        DeviceGuard guard(c->device);
         const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad};
         if (!c->gexec || memcmp(&key, &c->gkey, sizeof key) != 0) {
             // (re)capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
@@ -973,7 +992,7 @@ int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stre
 int zigp_elbo_grad_host(zigp_ctx* c, const double* theta, double* out, void* stream) {
     if (!c || !theta || !out) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     memcpy(c->theta_pin, theta, (size_t)c->theta_len * sizeof(double));
     CK(cudaMemcpyAsync(c->theta_dev, c->theta_pin, (size_t)c->theta_len * sizeof(double), cudaMemcpyHostToDevice, st));
     RUN(do_accumulate(c, c->theta_dev, st));
@@ -992,7 +1011,7 @@ int zigp_prior_kl_dev(zigp_ctx* c, const double* theta, double* out, void* strea
     if (!c || !theta || !out) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (c->kron) return kron_prior_kl(c, theta, out, st);
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     for (int l = 0; l < 2; l++) RUN(mstage_forward(c, l, theta, st));
     kl_out_kernel<<<1, 1, 0, st>>>(c->lat[0].kl, c->lat[1].kl, c->info, out);
@@ -1004,7 +1023,7 @@ int zigp_predict_dev(zigp_ctx* c, const double* theta, const double* Xnew, int64
     if (!c || !theta || !Xnew || !out9 || n_new <= 0) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if (c->kron) return kron_predict(c, theta, Xnew, n_new, out9, st);
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     for (int l = 0; l < 2; l++) RUN(mstage_forward(c, l, theta, st));
     for (long long n0 = 0; n0 < n_new; n0 += c->chunk) {
@@ -1021,22 +1040,34 @@ int zigp_predict_dev(zigp_ctx* c, const double* theta, const double* Xnew, int64
 int zigp_predict_host(zigp_ctx* c, const double* theta, const double* Xnew, int64_t n_new, double* out9, void* stream) {
     if (!c || !theta || !Xnew || !out9 || n_new <= 0) return ZIGP_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaSetDevice(c->device));
-    double *xd = nullptr, *od = nullptr;
-    CK(cudaMalloc((void**)&xd, (size_t)n_new * c->D * sizeof(double)));
-    if (cudaMalloc((void**)&od, (size_t)n_new * 9 * sizeof(double)) != cudaSuccess) { cudaFree(xd); c->err = "cudaMalloc failed in zigp_predict_host"; return ZIGP_ECUDA; }
-    int rc = ZIGP_OK;
-    auto body = [&]() -> int {
-        CK(cudaMemcpyAsync(c->theta_dev, theta, (size_t)c->theta_len * sizeof(double), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(xd, Xnew, (size_t)n_new * c->D * sizeof(double), cudaMemcpyHostToDevice, st));
-        RUN(zigp_predict_dev(c, c->theta_dev, xd, n_new, od, stream));
-        CK(cudaMemcpyAsync(out9, od, (size_t)n_new * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DeviceGuard guard(c->device);
+    if (n_new > c->pred_cap) {                 // context-owned staging buffers: repeated calls do not pay cudaMalloc / cudaFree
         CK(cudaStreamSynchronize(st));
-        return ZIGP_OK;
-    };
-    rc = body();
-    cudaFree(xd); cudaFree(od);
-    return rc;
+        cudaFree(c->pred_x); cudaFree(c->pred_o);
+        c->pred_x = c->pred_o = nullptr; c->pred_cap = 0;
+        CK(cudaMalloc((void**)&c->pred_x, (size_t)n_new * c->D * sizeof(double)));
+        CK(cudaMalloc((void**)&c->pred_o, (size_t)n_new * 9 * sizeof(double)));
+        c->pred_cap = n_new;
+    }
+    CK(cudaMemcpyAsync(c->theta_dev, theta, (size_t)c->theta_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->pred_x, Xnew, (size_t)n_new * c->D * sizeof(double), cudaMemcpyHostToDevice, st));
+    RUN(zigp_predict_dev(c, c->theta_dev, c->pred_x, n_new, c->pred_o, stream));
+    CK(cudaMemcpyAsync(out9, c->pred_o, (size_t)n_new * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int64_t info = 0;
+    RUN(zigp_read_info(c, &info, stream));     // synchronises the stream
+    if (info != 0) { not_pd_message(c, info); return ZIGP_ENOTPD; }
+    return ZIGP_OK;
+}
+
+int zigp_read_info(zigp_ctx* c, int64_t* info, void* stream) {
+    if (!c || !info) return ZIGP_EINVAL;
+    DeviceGuard guard(c->device);
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, c->info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    *info = h;
+    if (h != 0) not_pd_message(c, h);
+    return ZIGP_OK;
 }
 
 int zigp_debug_buffer(zigp_ctx* c, const char* name, int latent, double** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
@@ -1064,7 +1095,7 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
                     int kdim, int tri, double* stat_sq, void* stream) {
     if (!c || !In || !W || (!Out && !(engine != 0 && stat_sq)) || rows <= 0 || cols <= 0 || kdim <= 0 || tri < 0 || tri > 2) return ZIGP_EINVAL;   // int8 engine: Out may be null (statistics only)
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     if (engine == 0) {
         if (rows % 64 || cols % 64 || kdim % 32) { c->err = "zigp_debug_gemm: DMMA engine needs rows, cols % 64 == 0 and kdim % 32 == 0"; return ZIGP_EINVAL; }
         GemmArgs g{};
@@ -1098,10 +1129,20 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
     return ZIGP_OK;
 }
 
+int zigp_debug_int8_peak(zigp_ctx* c, int iters, int n, double* ops_per_launch, void* stream) {
+    if (!c || !ops_per_launch) return ZIGP_EINVAL;
+    DeviceGuard guard(c->device);
+    int n_sms = 0;
+    CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, c->device));
+    CK(oz::launch_i8_peak(iters, n, n_sms, ops_per_launch, (cudaStream_t)stream));
+    c->launches++;
+    return ZIGP_OK;
+}
+
 int zigp_set_engine(zigp_ctx* c, int engine) {
     if (!c || engine < 0 || engine > 1) return ZIGP_EINVAL;
     if (c->kron && engine == 1) { c->err = "zigp_set_engine: the int8 engine serves the dense path only"; return ZIGP_EINVAL; }
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     if (engine == 1 && !c->oz_ready) {
         if (!oz::encode_fn()) { c->err = "zigp_set_engine: cuTensorMapEncodeTiled not available from this driver"; return ZIGP_ECUDA; }
         if (std::max(c->lat[0].Mp, c->lat[1].Mp) > oz::MAX_ACC_K) { c->err = "zigp_set_engine: int8 engine supports up to 16384 inducing points per latent"; return ZIGP_EINVAL; }
@@ -1152,7 +1193,7 @@ int zigp_set_precision(zigp_ctx* c, int mode) {
 
 int zigp_set_profiling(zigp_ctx* c, int on) {
     if (!c) return ZIGP_EINVAL;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     c->prof.clear();
@@ -1162,7 +1203,7 @@ int zigp_set_profiling(zigp_ctx* c, int on) {
 
 int zigp_profile_read(zigp_ctx* c, double* ms_by_class, int64_t* launches_by_class, int n_classes) {
     if (!c || !ms_by_class || !launches_by_class || n_classes < PC_COUNT) return ZIGP_EINVAL;
-    CK(cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
     CK(cudaDeviceSynchronize());
     for (int i = 0; i < n_classes; i++) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
     for (auto& r : c->prof) {

@@ -32,6 +32,8 @@ SYMBOLS = {
     "zigp_prior_kl_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zigp_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "zigp_read_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "zigp_debug_int8_peak": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "zigp_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
     "zigp_get_engine": (C.c_int, [C.c_void_p]),
@@ -130,6 +132,20 @@ class Context:
         p, r, c, ld = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64()
         self.call("zigp_debug_buffer", name.encode(), int(latent), C.byref(p), C.byref(r), C.byref(c), C.byref(ld))
         return p.value, r.value, c.value, ld.value
+
+    def check_info(self, stream):
+        """raise NotPositiveDefiniteError if the Cholesky of the last call on `stream` failed (synchronises the stream)"""
+        info = C.c_int64()
+        self.call("zigp_read_info", C.byref(info), stream)
+        if info.value != 0:
+            msg = lib().zigp_last_error(self._h)
+            raise NotPositiveDefiniteError(msg.decode() if msg else "Kmm + jitter*I is not positive definite")
+
+    def int8_peak_launch(self, iters, n, stream):
+        """launch the int8 tensor-pipe issue loop once; returns the integer ops of the launch (the caller times it)"""
+        ops = C.c_double()
+        self.call("zigp_debug_int8_peak", int(iters), int(n), C.byref(ops), stream)
+        return ops.value
 
     def launch_count(self) -> int:
         return int(lib().zigp_launch_count(self._h))

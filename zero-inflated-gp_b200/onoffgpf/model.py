@@ -152,7 +152,7 @@ class OnOffSVGP(Parameterized):
         self.precision = precision or os.environ.get("ZIGP_PRECISION", "fp64")
         if self.precision != "fp64":
             self._ctx.set_precision(self.precision)
-        self._graph = _cabi.graph_default(graph, min(self.minibatch_size, self.num_data_local), distributed)
+        self._graph = _cabi.graph_default(graph, min(self.minibatch_size, self.num_data_local), self.distributed)
         if self._graph:
             self._ctx.set_graph(True)
         self._chunk_rows = int(chunk_rows)
@@ -202,8 +202,11 @@ class OnOffSVGP(Parameterized):
                 if getattr(self, "_graph", False):
                     self._Xb_buf, self._Yb_buf = self._Xb, self._Yb
         n_b = self._Xb.shape[0]
-        n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
-        scale = float(self.num_data) / float(n_global)        # onoffgpf/OnOffSVGP.py:119-120
+        # the global batch size is fixed by the shapes (full shard, or a fixed minibatch size per rank): one all-reduce at the first call
+        if getattr(self, "_n_global_for", None) != n_b:
+            self._n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
+            self._n_global_for = n_b
+        scale = float(self.num_data) / float(self._n_global)        # onoffgpf/OnOffSVGP.py:119-120
         self._ctx.call("zigp_set_data_dev", self._Xb.data_ptr(), self._Yb.data_ptr(), n_b, scale)
 
     def _evaluate(self, theta: torch.Tensor) -> torch.Tensor:
@@ -267,7 +270,7 @@ class OnOffSVGP(Parameterized):
             theta = self.pack_theta().contiguous()
             out9 = torch.empty((9, n), dtype=DTYPE, device=self.device)
             self._ctx.call("zigp_predict_dev", theta.data_ptr(), Xn.data_ptr(), n, out9.data_ptr(), self._stream())
-            torch.cuda.current_stream(self.device).synchronize()
+            self._ctx.check_info(self._stream())         # a failed Cholesky must not come back as NaN predictions (the reference raises)
             return tuple(out9[i].reshape(-1, 1) for i in range(9))
 
     def predict_onoffgp(self, Xnew):
@@ -350,7 +353,7 @@ class OnOffSVGP(Parameterized):
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        for k in ("_ctx", "_X_dev", "_Y_dev", "_Xb", "_Yb", "_last_out"):
+        for k in ("_ctx", "_X_dev", "_Y_dev", "_Xb", "_Yb", "_Xb_buf", "_Yb_buf", "_last_out", "_n_global", "_n_global_for"):
             d.pop(k, None)
         d["device"] = str(self.device)
         return d

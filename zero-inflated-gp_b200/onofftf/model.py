@@ -173,8 +173,10 @@ class OnOffKron(Parameterized):
                 if getattr(self, "_graph", False):
                     self._Xb_buf, self._Yb_buf = self._Xb, self._Yb
         n_b = self._Xb.shape[0]
-        n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
-        scale = float(self.num_data) / float(n_global)                   # scripts/onoff.py:311
+        if getattr(self, "_n_global_for", None) != n_b:                   # fixed by the shapes: one all-reduce, not one per evaluation
+            self._n_global = parallel.global_count(n_b, self.device) if self.distributed else n_b
+            self._n_global_for = n_b
+        scale = float(self.num_data) / float(self._n_global)             # scripts/onoff.py:311
         self._ctx.call("zigp_set_data_dev", self._Xb.data_ptr(), self._Yb.data_ptr(), n_b, scale)
 
     def _evaluate(self, theta):
@@ -239,7 +241,7 @@ class OnOffKron(Parameterized):
             theta = self.pack_theta().contiguous()
             out9 = torch.empty((9, n), dtype=DTYPE, device=self.device)
             self._ctx.call("zigp_predict_dev", theta.data_ptr(), Xn.data_ptr(), n, out9.data_ptr(), self._stream())
-            torch.cuda.current_stream(self.device).synchronize()
+            self._ctx.check_info(self._stream())         # a failed factor Cholesky raises instead of returning NaN predictions
             return tuple(out9[i].reshape(-1, 1) for i in range(9))
 
     # -- the script's optimiser set-up (scripts/onoff.py:325-350, 375-382) ------------------------------------------------
