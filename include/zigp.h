@@ -138,6 +138,11 @@ int zigp_set_precision(zigp_ctx* ctx, int mode);
  * cores, csrc/ozaki.cuh), so that the two engines can be compared on the same operands. */
 int zigp_debug_gemm(zigp_ctx* ctx, int engine, const double* In_dev, int64_t ldi, const double* W_dev, int64_t ldw, double* Out_dev, int64_t ldo,
                     int rows, int cols, int kdim, int tri, double* stat_sq_dev, void* stream);
+/* Test hook of the MN-major form of the int8 contraction (the rank update E += (gv A)^T A of the planes pipeline reads its operands this way):
+ * Out[r, c] = sum_k InT[k, r] WT[k, c], InT kdim x rows and WT kdim x cols row-major and dense; each operand is sliced elementwise under ONE
+ * power-of-two scale 2^e > 4 bound (|InT| <= bound_in, |WT| <= bound_w).  lower_only: skip tiles above the diagonal.  Synchronises the stream. */
+int zigp_debug_gemm_mn(zigp_ctx* ctx, const double* InT_dev, int64_t ldi, const double* WT_dev, int64_t ldw, double* Out_dev, int64_t ldo, int rows, int cols,
+                       int kdim, double bound_in, double bound_w, int lower_only, void* stream);
 /* Measurement hook: launches the int8 tensor-pipe issue loop (csrc/ozaki.cuh: i8_peak_kernel -- every SM issues 2 * iters tcgen05.mma kind::i8
  * of shape 128 x n x 32 on shared-memory-resident operands, no loads, no epilogue) on `stream` and returns the integer operations of that
  * launch.  The caller times it with CUDA events; bench.py uses the result as the measured int8 peak of `roofline`.  No reference counterpart. */

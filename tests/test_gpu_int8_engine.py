@@ -46,6 +46,55 @@ def test_int8_engine_matches_float64_matmul(rows, cols, K):
     assert torch.equal(out, In[:, :64])
 
 
+@pytest.mark.parametrize("rows,cols,K,ns", [(128, 64, 64, 7), (256, 128, 192, 7), (1024, 1024, 4096, 7), (384, 1024, 1024, 4)])
+def test_mn_major_contraction_matches_float64_matmul(rows, cols, K, ns):
+    """the rank update's operand form: planes [p][k][row] (the product's row index contiguous, k strided), both operands sliced under one
+    power-of-two scale -- Out = InT^T WT against fp64, error relative to K * bound_in * bound_w (the absolute error model of a fixed scale)"""
+    dev = torch.device("cuda:0")
+    ctx = _cabi.Context(0, 64, 64, 1, 1e-6, 512)
+    if ns == 4:
+        ctx.set_precision("fp32")
+    g = torch.Generator().manual_seed(rows + K + ns)
+    InT = torch.randn(K, rows, generator=g, dtype=torch.float64).to(dev)
+    WT = (torch.randn(K, cols, generator=g, dtype=torch.float64) * torch.exp(torch.randn(K, cols, generator=g, dtype=torch.float64))).to(dev)
+    Out = torch.full((rows, cols), float("nan"), dtype=torch.float64, device=dev)
+    bi, bw = float(InT.abs().max()), float(WT.abs().max())
+    ctx.call("zigp_debug_gemm_mn", InT.data_ptr(), rows, WT.data_ptr(), cols, Out.data_ptr(), cols, rows, cols, K, bi, bw, 0, torch.cuda.current_stream().cuda_stream)
+    ref = InT.T @ WT
+    err = float((Out - ref).abs().max()) / (K * bi * bw)
+    assert err < (1e-15 if ns == 7 else 2e-8), err
+    # exactness on integers: small integer operands survive slicing exactly, so the product is exact
+    A = torch.randint(-7, 8, (K, rows), generator=g).to(torch.float64).to(dev); B = torch.randint(-7, 8, (K, cols), generator=g).to(torch.float64).to(dev)
+    ctx.call("zigp_debug_gemm_mn", A.data_ptr(), rows, B.data_ptr(), cols, Out.data_ptr(), cols, rows, cols, K, 8.0, 8.0, 0, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(Out, A.T @ B)
+
+
+def test_planes_pipeline_equals_the_r1_pipeline(monkeypatch):
+    """ZIGP_OZ_PIPE=1 (default: A only as digit planes, gradient kernel over the planes, gv * A sliced point-major under one scale, MN-major rank
+    update) against ZIGP_OZ_PIPE=0 (fp64 A, transposed slicing with per-column scales): same ELBO to 1e-13 (the forward contractions are the
+    same launches) and the packed gradient to 1e-10 of its norm, on a ragged two-chunk problem with far-away points and an outlier row that
+    makes max |gv| 1e3 x the typical value"""
+    N, M, D = 70_001, 192, 2
+    X, Y = synth.make_data(N, D, 21)
+    X[:500] += 3.0
+    Y[1000] = 40.0
+    p = synth.make_params(M, M, D, 21)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZIGP_OZ_PIPE", mode)
+        m = synth.build_model(X, Y, p, engine="int8", chunk_rows=65536)
+        m.build_likelihood()
+        outs[mode] = m._last_out.cpu().numpy()
+        del m
+    a, b = outs["1"], outs["0"]
+    assert np.all(np.isfinite(a)) and a[3] == 0
+    assert abs(a[0] - b[0]) <= 1e-13 * abs(b[0])
+    ga, gb = synth.unpack_grad(a[4:], M, M, D), synth.unpack_grad(b[4:], M, M, D)
+    full = np.linalg.norm(b[4:])
+    for k in gb:
+        assert np.linalg.norm(ga[k] - gb[k]) <= 1e-10 * np.linalg.norm(gb[k]) + 1e-13 * full, (k, np.linalg.norm(ga[k] - gb[k]) / np.linalg.norm(gb[k]))
+
+
 def test_engines_agree_at_scale():
     """the two engines on the same 200 000-point problem: ELBO to 1e-12, every gradient block to 1e-10 of its norm"""
     N, M, D = 200_000, 256, 3
@@ -140,6 +189,7 @@ def test_reslicing_modes_agree(monkeypatch):
     X[:500] += 3.0                                   # points far from every inducing point: K and A rows ~ 1e-200
     p = synth.make_params(M, M, D, 21)
     outs = {}
+    monkeypatch.setenv("ZIGP_OZ_PIPE", "0")           # the fuse modes belong to the r1 pipeline (the planes pipeline always slices in the epilogue)
     for mode in ("0", "1", "2"):
         monkeypatch.setenv("ZIGP_OZ_FUSE", mode)
         m = synth.build_model(X, Y, p, engine="int8", chunk_rows=65536)

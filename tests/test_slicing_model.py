@@ -49,3 +49,25 @@ def test_truncated_slice_product_meets_its_bound():
         exact = sum(Fraction(float(a)) * Fraction(float(b)) for a, b in zip(x, y))
         bound = Fraction(K) * (Fraction(NS, 1 << (8 * NS)) + Fraction(2, 1 << 57))
         assert abs(approx - exact) <= bound
+
+
+def planes_to_f64(d, unit=1.0):
+    """model of ozaki.cuh:planes_to_f64x4<7>: the digit BYTES (two's complement) back to fp64 through H / L, the 2^52 bias and one FMA"""
+    u = [x & 0xFF for x in d]
+    H = ((u[0] << 16) | (u[1] << 8) | u[2]) ^ 0x808080
+    L = ((u[3] << 24) | (u[4] << 16) | (u[5] << 8) | u[6]) ^ 0x80808080
+    fh = float(H - 0x808080)                       # exact: |.| < 2^24
+    fl = float(L) - 2155905152.0                   # exact: uint32 - 0x80808080
+    return float(np.float64(fh) * np.float64(4294967296.0) + np.float64(fl)) * unit, (H - 0x808080) * (1 << 32) + (L - 0x80808080)
+
+
+def test_planes_back_to_float64():
+    """the inverse used by kgrad_planes_kernel: the 56-bit integer is recovered EXACTLY, and the fp64 value is V 2^-56 rounded once"""
+    rng = np.random.default_rng(2)
+    ts = np.concatenate([rng.uniform(-0.25, 0.25, 3000), rng.uniform(-0.25, 0.25, 500) * 1e-9, [0.0, 2.0 ** -56, -2.0 ** -56, 0.2499999999999999, -0.25 + 2.0 ** -54]])
+    for t in ts:
+        d, V = slice_bytes(float(t))
+        val, Vr = planes_to_f64(d, 2.0 ** -56)
+        assert Vr == V
+        assert Fraction(val) == Fraction(float(np.float64(V) * 2.0 ** -56)) or abs(Fraction(val) - Fraction(V, 1 << 56)) <= Fraction(1, 1 << 56) * Fraction(abs(V), 1 << 52)
+        assert abs(val - float(t)) <= 2.0 ** -56                    # within the slicing error (half a unit of the last digit) + one fp64 rounding

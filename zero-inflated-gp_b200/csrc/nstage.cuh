@@ -115,6 +115,8 @@ struct PointArgs {
     int precomputed;                  // 1: mean[]/vr[] already hold the moments (Kronecker path); 0: build them from the row stats
     int lik;                          // 0: on/off (two latents); 1: Gaussian, latent f only (scripts/svgp.py:201-203); 2: probit Bernoulli,
                                       //    latent f only (scripts/classifier.py:139-141, 210-217)
+    unsigned long long* gvmax[2];     // optional: max_n |gv_n| of the chunk per latent as a bit pattern (order-independent integer max); the int8
+                                      //    engine derives the power-of-two scale of gv * A from it (zeroed by the caller before the launch)
 };
 
 // single-latent comparison likelihoods: value and d/d(mean, var), d/d noise
@@ -174,6 +176,15 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
         } else {
             p.gm[0][r] = 0.0; p.gv[0][r] = 0.0;
             if (p.lik == 0) { p.gm[1][r] = 0.0; p.gv[1][r] = 0.0; }
+        }
+    }
+    if (p.gvmax[0]) {
+        // sgf / sgg are this row's gv_f / gv_g (0 for padding rows)
+        double mf = fabs(sgf), mg = fabs(sgg);
+        for (int o = 16; o; o >>= 1) { mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o)); mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, o)); }
+        if ((threadIdx.x & 31) == 0) {
+            if (mf > 0.0) atomicMax(p.gvmax[0], (unsigned long long)__double_as_longlong(mf));      // non-negative doubles order like their bit patterns
+            if (p.gvmax[1] && mg > 0.0) atomicMax(p.gvmax[1], (unsigned long long)__double_as_longlong(mg));
         }
     }
     double t0 = block_sum(ll, sh), t1 = block_sum(dn, sh), t2 = block_sum(sgf, sh), t3 = block_sum(sgg, sh);

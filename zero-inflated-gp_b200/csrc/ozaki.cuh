@@ -278,6 +278,166 @@ __global__ void __launch_bounds__(128) slice_cols_kernel(const double* __restric
     }
 }
 
+// ---- digit planes back to fp64 ----------------------------------------------------------------------------------------------------
+// inverse of slice_bytes<NS> for four consecutive elements: w[p] holds digit p of elements 0..3 in bytes 0..3.
+// NS = 7: the 56-bit integer V = sum_p d_p 256^(6-p) is rebuilt as (H - 0x808080) 2^32 + (L - 0x80808080) from the offset-binary bytes (digit
+// byte XOR 0x80), both halves converted exactly through the 2^52 bias; the final fused multiply-add rounds once to fp64.  NS = 4: V is the
+// int32 (U - 0x80808080).  Result = V * unit with unit = 2^(e - 8 NS), e the exponent of the operand's power-of-two scale.
+template <int NS>
+__device__ __forceinline__ void planes_to_f64x4(const uint32_t (&w)[NS], double unit, double (&out)[4]) {
+    static_assert(NS == 7 || NS == 4, "operands are sliced with 7 or 4 planes");
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (NS == 7) {
+            const uint32_t d0 = (w[0] >> (8 * j)) & 255u, d1 = (w[1] >> (8 * j)) & 255u, d2 = (w[2] >> (8 * j)) & 255u, d3 = (w[3] >> (8 * j)) & 255u;
+            const uint32_t d4 = (w[4] >> (8 * j)) & 255u, d5 = (w[5] >> (8 * j)) & 255u, d6 = (w[NS - 1] >> (8 * j)) & 255u;
+            const uint32_t H = ((d0 << 16) | (d1 << 8) | d2) ^ 0x00808080u;
+            const uint32_t L = ((d3 << 24) | (d4 << 16) | (d5 << 8) | d6) ^ 0x80808080u;
+            const double fh = __hiloint2double(0x43300000, (int)((uint32_t)((int)H - 0x00808080) ^ 0x80000000u)) - 4503601774854144.0;   // exact int32 -> double
+            const double fl = (__hiloint2double(0x43300000, (int)L) - 4503599627370496.0) - 2155905152.0;                                 // exact uint32 - 0x80808080
+            out[j] = fma(fh, 4294967296.0, fl) * unit;
+        } else {
+            const uint32_t d0 = (w[0] >> (8 * j)) & 255u, d1 = (w[1] >> (8 * j)) & 255u, d2 = (w[2] >> (8 * j)) & 255u, d3 = (w[3] >> (8 * j)) & 255u;
+            const uint32_t U = ((d0 << 24) | (d1 << 16) | (d2 << 8) | d3) ^ 0x80808080u;
+            const int v = (int)(U - 0x80808080u);
+            out[j] = (__hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0) * unit;
+        }
+    }
+}
+
+// elementwise slicing with ONE power-of-two scale: planes[p][n][m] = digit p of X[n][m] * inv (test helper of the MN-major contraction and the
+// reference implementation of what kgrad_planes_kernel writes).  ld = leading dimension of X and of the planes; m % 4 == 0.
+template <int NS>
+__global__ void __launch_bounds__(256) slice_fixed_kernel(const double* __restrict__ X, long long ld, long long n, int m, double inv, int8_t* __restrict__ planes,
+                                                           long long plane_stride) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 consecutive elements
+    const long long per_row = m / 4;
+    if (q >= n * per_row) return;
+    const long long r = q / per_row; const int c = (int)(q % per_row) * 4;
+    const double4 v = *reinterpret_cast<const double4*>(X + r * ld + c);
+    const double t[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) slice_bytes<NS>(t[j], lo[j], hi[j]);
+#pragma unroll
+    for (int p = 0; p < NS; p++) *reinterpret_cast<uint32_t*>(planes + (long long)p * plane_stride + r * ld + c) = plane_word4<NS>(p, lo, hi);
+}
+
+// ---- Kmn-side gradient sums from the digit planes (int8 engine, planes pipeline) -------------------------------------------------------
+// One pass per chunk and latent: reads K (fp64), Y = G A (fp64) and the digit planes of A (the operand the contractions used: A is never
+// stored as fp64), forms  G = (gm_n beta_m - 2 gv_n Y) K  and reduces  S0 = sum G, S1 = sum G (x - z), Q = sum G (x - z)^2, a = sum gm_n A
+// per column into this CTA's slot (as kgrad_kernel, nstage.cuh), and WRITES the digit planes of gv_n A[n, m] -- point-major, [p][n][m] --
+// under ONE power-of-two scale 2^e > 4 sqrt(var) max_n |gv_n| (|A_nm| <= sqrt(var); the maximum comes from the likelihood kernel).  The rank
+// update E += (gv A)^T A then contracts those planes with A's own planes as MN-major operands: no transposed copies, no separate slicing pass.
+// Thread = 4 consecutive columns (4-byte plane words, 32-byte fp64 loads), warp = 128 columns, CTA = 512 columns x KGP_ROWS rows.
+constexpr int KGP_ROWS = 128;
+struct KgradPArgs {
+    const double* K; const double* Y; long long ld;
+    const int8_t* Ap; int8_t* Awp; long long pstride;          // planes of A (in) and of gv * A (out), plane stride in bytes
+    const double* gm; const double* gv; const double* beta;
+    const double* X; long long n0; int nvalid, rows;
+    const double* Z; int M, D, Mp;
+    const double* var;                                         // kernel variance (device scalar): A was sliced under 2^e > 4 sqrt(var)
+    const unsigned long long* gvmax;                           // bit pattern of max_n |gv_n| over the chunk
+    double* partial;                                           // [nslots][2 + 2 D][Mp]
+    double* a_scale; double* aw_scale;                         // out [Mp]: the two scales, as per-row scale vectors of the rank update's operands
+};
+
+template <int NS, int DT>
+__global__ void __launch_bounds__(128, (DT <= 4 ? 3 : 1)) kgrad_planes_kernel(const KgradPArgs p) {
+    __shared__ double sx[KGP_ROWS][DT];
+    __shared__ double sgm[KGP_ROWS], sgv[KGP_ROWS];
+    const int m0 = blockIdx.x * 512 + threadIdx.x * 4;
+    const int r0 = blockIdx.y * KGP_ROWS;
+    const int nr = max(0, min(KGP_ROWS, p.nvalid - r0));
+    const int nrow = min(KGP_ROWS, p.rows - r0);                       // rows of this block inside the padded chunk
+    for (int e = threadIdx.x; e < nr * p.D; e += 128) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
+    for (int e = threadIdx.x; e < nr; e += 128) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
+    __syncthreads();
+    if (m0 >= p.Mp) return;
+    const double sd = sqrt(p.var[0]);
+    const int ea = ilogb(sd) + EOFF;
+    const double gmx = __longlong_as_double((long long)p.gvmax[0]);
+    const int ew = (gmx > 0.0) ? ilogb(sd * gmx) + EOFF : 0;
+    const double unit_a = scalbn(1.0, ea - 8 * NS), inv_w = scalbn(1.0, -ew);
+    if (blockIdx.y == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { p.a_scale[m0 + j] = scalbn(1.0, ea); p.aw_scale[m0 + j] = scalbn(1.0, ew); }
+    }
+    double z[4][DT], bm[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        bm[j] = p.beta[m0 + j];
+#pragma unroll
+        for (int d = 0; d < DT; d++) z[j][d] = (d < p.D && m0 + j < p.M) ? p.Z[(long long)(m0 + j) * p.D + d] : 0.0;
+    }
+    double s0[4] = {0, 0, 0, 0}, am[4] = {0, 0, 0, 0}, s1[4][DT], q[4][DT];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int d = 0; d < DT; d++) { s1[j][d] = 0.0; q[j][d] = 0.0; }
+    const long long base = (long long)r0 * p.ld + m0;
+#pragma unroll 2
+    for (int r = 0; r < nr; r++) {
+        const long long o = base + (long long)r * p.ld;
+        uint32_t wa[NS];
+#pragma unroll
+        for (int pl = 0; pl < NS; pl++) wa[pl] = *reinterpret_cast<const uint32_t*>(p.Ap + (long long)pl * p.pstride + o);
+        const double4 kk = *reinterpret_cast<const double4*>(p.K + o);
+        const double4 yy = *reinterpret_cast<const double4*>(p.Y + o);
+        double a[4];
+        planes_to_f64x4<NS>(wa, unit_a, a);
+        const double k[4] = {kk.x, kk.y, kk.z, kk.w}, y[4] = {yy.x, yy.y, yy.z, yy.w};
+        const double gmr = sgm[r], gvr = sgv[r];
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            slice_bytes<NS>(gvr * a[j] * inv_w, lo[j], hi[j]);
+            const double G = (gmr * bm[j] - 2.0 * gvr * y[j]) * k[j];
+            s0[j] += G;
+            am[j] = fma(gmr, a[j], am[j]);
+#pragma unroll
+            for (int d = 0; d < DT; d++) {
+                if (d < p.D) { const double df = sx[r][d] - z[j][d]; s1[j][d] = fma(G, df, s1[j][d]); q[j][d] = fma(G * df, df, q[j][d]); }
+            }
+        }
+#pragma unroll
+        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(p.Awp + (long long)pl * p.pstride + o) = plane_word4<NS>(pl, lo, hi);
+    }
+    for (int r = nr; r < nrow; r++) {                                  // padding rows of the chunk: gv * A = 0 -> all-zero digits
+#pragma unroll
+        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(p.Awp + (long long)pl * p.pstride + base + (long long)r * p.ld) = 0u;
+    }
+    if (nr <= 0) return;
+    double* out = p.partial + (long long)blockIdx.y * (2 + 2 * p.D) * p.Mp + m0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        out[j] += s0[j];
+        out[(long long)p.Mp + j] += am[j];
+#pragma unroll
+        for (int d = 0; d < DT; d++) {
+            if (d < p.D) { out[(long long)(2 + d) * p.Mp + j] += s1[j][d]; out[(long long)(2 + p.D + d) * p.Mp + j] += q[j][d]; }
+        }
+    }
+}
+
+inline cudaError_t launch_kgrad_planes(int ns, const KgradPArgs& k, cudaStream_t st) {
+    const dim3 grid((k.Mp + 511) / 512, (k.rows + KGP_ROWS - 1) / KGP_ROWS);
+#define ZIGP_KGP(NSV, DTV) kgrad_planes_kernel<NSV, DTV><<<grid, 128, 0, st>>>(k)
+#define ZIGP_KGP_D(NSV)                                  \
+    switch (k.D) {                                       \
+        case 1: ZIGP_KGP(NSV, 1); break;                 \
+        case 2: ZIGP_KGP(NSV, 2); break;                 \
+        case 3: ZIGP_KGP(NSV, 3); break;                 \
+        case 4: ZIGP_KGP(NSV, 4); break;                 \
+        default: ZIGP_KGP(NSV, ZIGP_MAX_D); break;       \
+    }
+    if (ns == NS64) { ZIGP_KGP_D(NS64) } else if (ns == NS32) { ZIGP_KGP_D(NS32) } else return cudaErrorInvalidValue;
+#undef ZIGP_KGP_D
+#undef ZIGP_KGP
+    return cudaGetLastError();
+}
+
 // ---- the contraction ------------------------------------------------------------------------------------------------------
 struct OzArgs {
     const double* rscale;   // [rows]  2^e of the In rows
@@ -311,7 +471,11 @@ __device__ long long oz_trace[8 * 256];
 #define OZ_TRACE(slot, idx) do { } while (0)
 #endif
 
-template <int NS, int CL>
+// MNM = true: both operands MN-major -- the planes are stored [plane][k][row] (the row / column index of the product contiguous, k strided),
+// which is how the point-major digit planes of A and gv * A look to the rank update E += (gv A)^T A (k = point index): no transposed copies.
+// A stage is then a TMA box {128 or 64 bytes of rows, 64 k, planes}; the shared-memory descriptors walk k in groups of 8 rows (SBO) and the
+// concatenated planes of the column operand in steps of LBO = one plane.  Stage sizes, barriers, tile geometry and the epilogue are shared.
+template <int NS, int CL, bool MNM = false>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                                                                       const __grid_constant__ CUtensorMap mapB, const OzArgs g) {
     constexpr int A_STAGE = Cfg<NS>::A_STAGE, B_STAGE = Cfg<NS>::B_STAGE, OSTAGES = Cfg<NS>::STAGES;
@@ -413,9 +577,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                     tc05::mbar_arrive_expect_tx(&full[s], A_STAGE + (active ? B_STAGE : 0));
                     uint8_t* dstA = sA + (size_t)s * A_STAGE + (size_t)rank * PL * OBM * OBK;
                     const CUtensorMap* mA = (NS % CL != 0 && rank == CL - 1) ? &mapA2 : &mapA;
-                    if (CL > 1) tc05::tma_load_3d_mcast(dstA, mA, &full[s], k0, row0, (int)rank * PL, CMASK);
-                    else tc05::tma_load_3d(dstA, mA, &full[s], k0, row0, 0);
-                    if (active) tc05::tma_load_3d(sB + (size_t)s * B_STAGE, &mapB, &full[s], k0, col0, 0);
+                    const int ca0 = MNM ? row0 : k0, ca1 = MNM ? k0 : row0, cb0 = MNM ? col0 : k0, cb1 = MNM ? k0 : col0;
+                    if (CL > 1) tc05::tma_load_3d_mcast(dstA, mA, &full[s], ca0, ca1, (int)rank * PL, CMASK);
+                    else tc05::tma_load_3d(dstA, mA, &full[s], ca0, ca1, 0);
+                    if (active) tc05::tma_load_3d(sB + (size_t)s * B_STAGE, &mapB, &full[s], cb0, cb1, 0);
                 }
             }
         }
@@ -446,12 +611,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                         for (int ks = 0; ks < OBK / UK; ks++) {
 #pragma unroll
                             for (int p = 0; p < NS; p++) {
-                                const uint64_t da = tc05::smem_desc_kmajor<OBK>(a_base + p * (OBM * OBK) + ks * UK);
+                                // K-major: plane p = 128 rows x 64 k bytes, the k sub-step advances 32 bytes inside the rows.
+                                // MN-major: plane p = 64 k rows x 128 row bytes (column operand: x 64 bytes), the k sub-step advances 32 rows.
+                                const uint64_t da = MNM ? tc05::smem_desc_mnmajor<OBM>(a_base + p * (OBM * OBK) + ks * UK * OBM, OBM * OBK)
+                                                        : tc05::smem_desc_kmajor<OBK>(a_base + p * (OBM * OBK) + ks * UK);
                                 int nrem = (NS - p) * OBN, off = 0;
                                 while (nrem > 0) {
                                     const int n = nrem > 256 ? 256 : nrem;
-                                    const uint64_t db = tc05::smem_desc_kmajor<OBK>(b_base + off * OBK + ks * UK);
-                                    tc05::mma_i8(tmem_base + (uint32_t)(p * OBN + off), da, db, tc05::idesc_i8(OBM, n), (first && ks == 0 && p == 0) ? 0u : 1u);
+                                    const uint64_t db = MNM ? tc05::smem_desc_mnmajor<OBN>(b_base + off * OBK + ks * UK * OBN, OBN * OBK)
+                                                            : tc05::smem_desc_kmajor<OBK>(b_base + off * OBK + ks * UK);
+                                    tc05::mma_i8(tmem_base + (uint32_t)(p * OBN + off), da, db, MNM ? tc05::idesc_i8_mn(OBM, n) : tc05::idesc_i8(OBM, n),
+                                                 (first && ks == 0 && p == 0) ? 0u : 1u);
                                     off += n; nrem -= n;
                                 }
                             }
@@ -699,13 +869,31 @@ inline bool make_plane_map(CUtensorMap* map, const int8_t* planes, long long K, 
               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct OzOperand {                   // a sliced matrix: ns planes of nrows x K int8 + one power-of-two scale per row
+// tensor map over MN-major slice planes [ns][K][ld] (int8; the product's row / column index contiguous with leading dimension ld, k strided):
+// box = box_cols bytes x OBK k-rows x box_planes, swizzle = box_cols bytes (128 for the row operand, 64 for the column operand)
+inline bool make_plane_map_mn(CUtensorMap* map, const int8_t* planes, long long ld, long long ncols, long long K, long long plane_stride, int ns, int box_cols,
+                              int box_planes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)K, (cuuint64_t)ns};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)OBK, (cuuint32_t)box_planes};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// a sliced matrix: ns planes of int8 + one power-of-two scale per row.  K-major (default): planes[p][row][k], K = row length (k contiguous).
+// MN-major (mn = true): planes[p][k][row] with leading dimension ld (rows contiguous) -- the operands of the rank update over the point index.
+struct OzOperand {
     const int8_t* planes; long long K; long long nrows; long long plane_stride; const double* scale;
+    bool mn = false; long long ld = 0;
 };
 
-template <int NS, int CL>
+template <int NS, int CL, bool MNM = false>
 inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, OzArgs g, cudaStream_t st) {
-    auto kern = ozaki_gemm_kernel<NS, CL>;
+    auto kern = ozaki_gemm_kernel<NS, CL, MNM>;
     // per-device opt-in to the dynamic shared memory size and per-device SM count (one process may hold contexts on several GPUs)
     static int sms_of[MAX_DEVICES] = {};
     int dev = 0;
@@ -721,9 +909,15 @@ inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, O
     }
     CUtensorMap ma, ma2, mb;
     constexpr int PL = (NS + CL - 1) / CL, PL2 = NS - PL * (CL - 1);
-    if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, NS, OBM, PL)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&ma2, A.planes, A.K, A.nrows, A.plane_stride, NS, OBM, PL2 > 0 ? PL2 : PL)) return cudaErrorInvalidValue;
-    if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, NS, OBN, NS)) return cudaErrorInvalidValue;
+    if (MNM) {
+        if (!make_plane_map_mn(&ma, A.planes, A.ld, A.nrows, A.K, A.plane_stride, NS, OBM, PL)) return cudaErrorInvalidValue;
+        if (!make_plane_map_mn(&ma2, A.planes, A.ld, A.nrows, A.K, A.plane_stride, NS, OBM, PL2 > 0 ? PL2 : PL)) return cudaErrorInvalidValue;
+        if (!make_plane_map_mn(&mb, B.planes, B.ld, B.nrows, B.K, B.plane_stride, NS, OBN, NS)) return cudaErrorInvalidValue;
+    } else {
+        if (!make_plane_map(&ma, A.planes, A.K, A.nrows, A.plane_stride, NS, OBM, PL)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&ma2, A.planes, A.K, A.nrows, A.plane_stride, NS, OBM, PL2 > 0 ? PL2 : PL)) return cudaErrorInvalidValue;
+        if (!make_plane_map(&mb, B.planes, B.K, B.nrows, B.plane_stride, NS, OBN, NS)) return cudaErrorInvalidValue;
+    }
     g.rscale = A.scale; g.cscale = B.scale;
     if (g.nsplit < 1) g.nsplit = 1;
     if (g.nsplit > g.kdim / OBK) g.nsplit = std::max(1, g.kdim / OBK);     // every split owns at least one k block (short last chunk); the other split buffers stay zero
@@ -745,6 +939,14 @@ inline cudaError_t launch_ozaki_gemm_t(const OzOperand& A, const OzOperand& B, O
 // ns = 7 (fp64 precision) or 4 (fp32-class precision); operands must have been sliced with the same ns
 inline cudaError_t launch_ozaki_gemm(int ns, const OzOperand& A, const OzOperand& B, const OzArgs& g, cudaStream_t st) {
     const bool pair = ZIGP_OZ_CL >= 2 && (g.cols / OBN) % 2 == 0;
+    if (A.mn != B.mn) return cudaErrorInvalidValue;
+    if (A.mn) {          // MN-major operands (rank update from point-major planes): 7, 6 (top planes of 7) or 4 slices
+        if (g.sl_bound2) return cudaErrorInvalidValue;
+        if (ns == NS64) return pair ? launch_ozaki_gemm_t<NS64, 2, true>(A, B, g, st) : launch_ozaki_gemm_t<NS64, 1, true>(A, B, g, st);
+        if (ns == NSG) return pair ? launch_ozaki_gemm_t<NSG, 2, true>(A, B, g, st) : launch_ozaki_gemm_t<NSG, 1, true>(A, B, g, st);
+        if (ns == NS32) return pair ? launch_ozaki_gemm_t<NS32, 2, true>(A, B, g, st) : launch_ozaki_gemm_t<NS32, 1, true>(A, B, g, st);
+        return cudaErrorInvalidValue;
+    }
     if (ns == NS64) return pair ? launch_ozaki_gemm_t<NS64, 2>(A, B, g, st) : launch_ozaki_gemm_t<NS64, 1>(A, B, g, st);
     // six slices: the top six planes of operands sliced with seven (21 slice products, three pipeline stages) -- gradient-side contractions of
     // the mixed mode (zigp_set_precision(ctx, 2)); no fused re-slicing in this instance

@@ -157,12 +157,31 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr) {
     return d;
 }
 
+// Shared-memory matrix descriptor, MN-major operand (the M / N index is the contiguous one; k runs over rows of SW bytes): the tile is
+// [k rows][SW bytes of consecutive M / N elements], 8-row groups packed densely, exactly what a TMA box {SW, rows, ..} with the SW-byte swizzle
+// writes.  Canonical form (CUTLASS make_umma_desc<Major::MN>, units of 16 bytes): ((SW/16, n), (8, k)) : ((1, LBO), (SW/16, SBO)) --
+// LBO = byte distance between consecutive SW-byte atoms along M / N (for operands wider than SW bytes, e.g. concatenated planes),
+// SBO = byte distance between consecutive groups of 8 k-rows (= 8 * SW when the rows are dense).
+template <int SW>
+__device__ __forceinline__ uint64_t smem_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+    constexpr uint64_t layout = (SW == 32) ? 6 : (SW == 64) ? 4 : 2;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((8 * SW) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
 // Instruction descriptor, kind::i8, signed 8-bit A and B (both K-major), int32 accumulator, M x N tile.
 // Bits: [4,6) D format (2 = S32), [7,10) A format (1 = S8), [10,13) B format (1 = S8), 15 / 16 A / B major (0 = K),
 // [17,23) N >> 3, [24,29) M >> 4.
 __host__ __device__ __forceinline__ uint32_t idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with both operands MN-major (bits 15 / 16)
+__host__ __device__ __forceinline__ uint32_t idesc_i8_mn(int M, int N) { return idesc_i8(M, N) | (1u << 15) | (1u << 16); }
 
 }  // namespace tc05
 }  // namespace zigp

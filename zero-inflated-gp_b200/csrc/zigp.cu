@@ -48,6 +48,7 @@ struct Latent {
     int8_t *oz_in = nullptr, *oz_inA = nullptr, *oz_colA = nullptr, *oz_colAw = nullptr;
     double *oz_rs = nullptr, *oz_rsA = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
     unsigned long long* oz_colmax = nullptr;
+    unsigned long long* oz_gvmax = nullptr;       // planes pipeline: max_n |gv_n| of the current chunk (bit pattern), from the likelihood kernel
     int nsplit_oz = 4;
 };
 
@@ -108,6 +109,12 @@ struct zigp_ctx {
     // contraction engine: 0 = DMMA (gemm_f64.cuh), 1 = fp64 on the int8 tensor cores (ozaki.cuh); dense path only
     int engine = 0;
     bool oz_ready = false;
+    // int8 pipeline per chunk and latent (ZIGP_OZ_PIPE):
+    //   1 (default) "planes": A exists only as digit planes (written by the A product's epilogue); the Kmn-side gradient kernel reads them and
+    //      writes the planes of gv * A point-major under one power-of-two scale; the rank update contracts the two plane sets as MN-major
+    //      operands (no transposed copies, no slice_cols pass, no fp64 A).
+    //   0 "r1": fp64 A + planes, kgrad_kernel + slice_cols_kernel (transposed planes, per-column scales), K-major rank update.
+    int oz_pipe = 1;
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
     int oz_ns_grad = 0;            // mixed mode: slices used by the gradient-only contractions (Y = G A, rank update); 0 = oz_ns
     int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
@@ -401,8 +408,9 @@ int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long
             c->launches++;
         }
         // A = K T^T, |A|^2, A.alpha_w; the epilogue re-slices A for the next products (and, oz_fuse == 2, for the rank update)
-        const int fuse = c->oz_fuse >= 2 && !need_bwd ? 1 : c->oz_fuse;
-        RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
+        const int fuse = c->oz_pipe ? 1 : (c->oz_fuse >= 2 && !need_bwd ? 1 : c->oz_fuse);
+        // planes pipeline: no fp64 A at all -- its only readers were the gradient kernel and the transposed slicer
+        RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, c->oz_pipe ? nullptr : L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
         if (!fuse) RUN(oz_slice_A(c, L, rows, Mp, st));
         RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
         if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));
@@ -444,6 +452,12 @@ int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long lon
     }
     p.noise = theta + 2 * c->D + 2;
     p.Y = Y; p.n0 = n0; p.nvalid = Y ? nvalid : 0; p.rows = rows; p.scale = c->scale; p.partial = c->pt_partial;
+    if (Y && c->engine == 1 && c->oz_pipe && rows % oz::OBM == 0) {
+        for (int l = 0; l < 2; l++) {
+            p.gvmax[l] = c->lat[l].oz_gvmax;
+            CK(cudaMemsetAsync(c->lat[l].oz_gvmax, 0, sizeof(unsigned long long), st));
+        }
+    }
     ProfScope ps(c, PC_POINT, st);
     point_kernel<<<rows / 256, 256, 0, st>>>(p);
     LAUNCHED();
@@ -454,6 +468,30 @@ int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long lon
 int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nvalid, int rows, cudaStream_t st) {
     const int D = c->D;
     Latent& L = c->lat[l];
+    if (c->engine == 1 && c->oz_pipe && rows % oz::OBM == 0) {
+        // planes pipeline: one pass over K, Y and A's digit planes -> gradient sums + digit planes of gv * A (point-major), then the rank
+        // update E += (gv A)^T A straight from the two point-major plane sets (MN-major operands, k = point index)
+        const long long pstride = (long long)rows * L.Mp;
+        oz::KgradPArgs k{};
+        k.K = L.Kb; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = pstride;
+        k.gm = L.gm; k.gv = L.gv; k.beta = L.beta; k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows;
+        k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.var = theta + L.off_var; k.gvmax = L.oz_gvmax;
+        k.partial = L.kg_partial; k.a_scale = L.oz_csA; k.aw_scale = L.oz_csAw;
+        {
+            ProfScope ps(c, PC_KGRAD, st);
+            CK(oz::launch_kgrad_planes(c->oz_ns, k, st));
+            c->launches++;
+        }
+        oz::OzOperand A{L.oz_colAw, rows, L.Mp, pstride, L.oz_csAw, true, L.Mp};
+        oz::OzOperand B{L.oz_inA, rows, L.Mp, pstride, L.oz_csA, true, L.Mp};
+        oz::OzArgs a{};
+        a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
+        a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
+        ProfScope ps(c, PC_SYRK, st);
+        CK(oz::launch_ozaki_gemm((c->oz_ns_grad && c->oz_ns == oz::NS64) ? c->oz_ns_grad : c->oz_ns, A, B, a, st));
+        c->launches++;
+        return 0;
+    }
     KgradArgs k{};
     k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
     k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows; k.Aw = L.Vb; k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.partial = L.kg_partial;
@@ -820,6 +858,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     }
     // default engine: fp64 on the int8 tensor cores; ZIGP_ENGINE=dmma (or zigp_set_engine(ctx, 0)) selects the DMMA engine
     if (const char* fz = getenv("ZIGP_OZ_FUSE")) c->oz_fuse = atoi(fz);
+    if (const char* pz = getenv("ZIGP_OZ_PIPE")) c->oz_pipe = atoi(pz) != 0;
     const char* env = getenv("ZIGP_ENGINE");
     if (!(env && std::string(env) == "dmma")) {
         // no silent downgrade: a context that cannot set up its default engine fails to create (ZIGP_ENGINE=dmma asks for the DMMA engine)
@@ -957,7 +996,7 @@ int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if (c->graph_on && !c->profiling && c->has_data) {
         DeviceGuard guard(c->device);
-        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad};
+        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad + 256 * c->oz_pipe};
         if (!c->gexec || memcmp(&key, &c->gkey, sizeof key) != 0) {
             // (re)capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
             if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
@@ -1129,6 +1168,49 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
     return ZIGP_OK;
 }
 
+// Test hook of the MN-major contraction: Out[r, c] = sum_k InT[k, r] WT[k, c] with both operands sliced elementwise under one power-of-two
+// scale each (2^e > 4 bound), planes [p][k][row] -- the layout of the rank update's operands in the planes pipeline.
+int zigp_debug_gemm_mn(zigp_ctx* c, const double* InT, int64_t ldi, const double* WT, int64_t ldw, double* Out, int64_t ldo, int rows, int cols, int kdim,
+                       double bound_in, double bound_w, int lower_only, void* stream) {
+    if (!c || !InT || !WT || !Out || rows <= 0 || cols <= 0 || kdim <= 0 || !(bound_in > 0.0) || !(bound_w > 0.0)) return ZIGP_EINVAL;
+    if (rows % oz::OBM || cols % oz::OBN || kdim % oz::OBK || ldi != rows || ldw != cols) {
+        c->err = "zigp_debug_gemm_mn: needs rows % 128 == 0, cols % 64 == 0, kdim % 64 == 0 and dense operands (ld == rows / cols)";
+        return ZIGP_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceGuard guard(c->device);
+    const int ns = c->oz_ns;
+    int8_t *pa = nullptr, *pb = nullptr; double *sa = nullptr, *sb = nullptr;
+    CK(cudaMalloc((void**)&pa, (size_t)ns * rows * kdim)); CK(cudaMalloc((void**)&pb, (size_t)ns * cols * kdim));
+    CK(cudaMalloc((void**)&sa, (size_t)rows * 8)); CK(cudaMalloc((void**)&sb, (size_t)cols * 8));
+    const int ea = ilogb(bound_in) + oz::EOFF, eb = ilogb(bound_w) + oz::EOFF;
+    std::vector<double> ha(rows, scalbn(1.0, ea)), hb(cols, scalbn(1.0, eb));
+    int rc = ZIGP_OK;
+    auto body = [&]() -> int {
+        CK(cudaMemcpyAsync(sa, ha.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sb, hb.data(), (size_t)cols * 8, cudaMemcpyHostToDevice, st));
+        const long long qa = (long long)kdim * rows / 4, qb = (long long)kdim * cols / 4;
+        if (ns == oz::NS64) {
+            oz::slice_fixed_kernel<oz::NS64><<<(unsigned)((qa + 255) / 256), 256, 0, st>>>(InT, ldi, kdim, rows, scalbn(1.0, -ea), pa, (long long)rows * kdim);
+            oz::slice_fixed_kernel<oz::NS64><<<(unsigned)((qb + 255) / 256), 256, 0, st>>>(WT, ldw, kdim, cols, scalbn(1.0, -eb), pb, (long long)cols * kdim);
+        } else {
+            oz::slice_fixed_kernel<oz::NS32><<<(unsigned)((qa + 255) / 256), 256, 0, st>>>(InT, ldi, kdim, rows, scalbn(1.0, -ea), pa, (long long)rows * kdim);
+            oz::slice_fixed_kernel<oz::NS32><<<(unsigned)((qb + 255) / 256), 256, 0, st>>>(WT, ldw, kdim, cols, scalbn(1.0, -eb), pb, (long long)cols * kdim);
+        }
+        CK(cudaGetLastError());
+        oz::OzOperand A{pa, kdim, rows, (long long)rows * kdim, sa, true, rows}, B{pb, kdim, cols, (long long)cols * kdim, sb, true, cols};
+        oz::OzArgs g{};
+        g.Out = Out; g.ldo = ldo; g.alpha = 1.0; g.beta = 0.0; g.rows = rows; g.cols = cols; g.kdim = kdim; g.tri = TRI_FULL; g.nsplit = 1; g.lower_only = lower_only;
+        CK(oz::launch_ozaki_gemm(ns, A, B, g, st));
+        c->launches += 3;
+        CK(cudaStreamSynchronize(st));
+        return ZIGP_OK;
+    };
+    rc = body();
+    cudaFree(pa); cudaFree(pb); cudaFree(sa); cudaFree(sb);
+    return rc;
+}
+
 int zigp_debug_int8_peak(zigp_ctx* c, int iters, int n, double* ops_per_launch, void* stream) {
     if (!c || !ops_per_launch) return ZIGP_EINVAL;
     DeviceGuard guard(c->device);
@@ -1155,6 +1237,8 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
             RUN(balloc((void**)&L.oz_colA, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colAw, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colmax, (size_t)2 * L.Mp * sizeof(unsigned long long)));
+            RUN(balloc((void**)&L.oz_gvmax, 2 * sizeof(unsigned long long)));
+            CK(cudaMemset(L.oz_gvmax, 0, 2 * sizeof(unsigned long long)));
             DA(L.oz_rs, chunk); DA(L.oz_rsA, chunk); DA(L.oz_csA, L.Mp); DA(L.oz_csAw, L.Mp);
             for (int i = 0; i < 3; i++) {
                 RUN(balloc((void**)&L.ozW[i], (size_t)oz::NS64 * L.Mp * L.Mp));

@@ -33,6 +33,8 @@ SYMBOLS = {
     "zigp_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_read_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "zigp_debug_gemm_mn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                     C.c_int, C.c_void_p]),
     "zigp_debug_int8_peak": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "zigp_debug_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "zigp_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
