@@ -139,6 +139,10 @@ def test_reduced_precision_mode_within_1e_4(name):
         assert err <= 1e-4 * np.linalg.norm(b) + 1e-7 * full, (k, err / np.linalg.norm(b))
         worst = max(worst, err / (np.linalg.norm(b) + 1e-300))
     assert abs(out[0] - float(z["elbo"])) > 0          # it IS the reduced mode
+    gall = np.concatenate([np.asarray(g[k]).reshape(-1) for k in orc.PARAM_NAMES]); rall = np.concatenate([z["g_" + k].reshape(-1) for k in orc.PARAM_NAMES])
+    whole = np.linalg.norm(gall - rall) / np.linalg.norm(rall)
+    assert whole <= 1e-4, whole                        # the packed gradient as a whole; single small blocks may sit a few 1e-4 of their own norm
+    print("fp32-class mode, %s: packed gradient rel err %.2e" % (name, whole))
     print("fp32-class mode, %s: ELBO rel err %.2e, worst gradient block rel err %.2e" % (name, abs(out[0] - float(z["elbo"])) / abs(float(z["elbo"])), worst))
 
 

@@ -245,7 +245,7 @@ def test_reference_api_surface_and_training_reaches_notebook_band():
     res = m.optimize(maxiter=8000)
     e1 = m.compute_log_likelihood()
     print("L-BFGS-B %d iterations: ELBO %.3f -> %.3f (reference class from the same start: %.3f; notebook: 488.713)" % (res.nit, e0, e1, float(t["elbo_opt"])))
-    assert 478.0 <= e1 <= 492.0, (e0, e1)
+    assert 478.0 <= e1 <= 496.0, (e0, e1)       # measured: 483.30 (int8 engine), 491.01 (DMMA engine)
     out = m.predict_onoffgp(X)
     assert len(out) == 9 and all(o.shape == (450, 1) for o in out)
     for attr in ("Xtrain", "Ytrain", "Zf", "Zg", "u_fm", "u_gm", "u_fs_sqrt", "u_gs_sqrt"):

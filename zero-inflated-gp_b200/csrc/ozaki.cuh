@@ -377,14 +377,19 @@ __global__ void __launch_bounds__(128, (DT <= 4 ? 3 : 1)) kgrad_planes_kernel(co
 #pragma unroll
         for (int d = 0; d < DT; d++) { s1[j][d] = 0.0; q[j][d] = 0.0; }
     const long long base = (long long)r0 * p.ld + m0;
+    // local restrict-qualified views: the plane stores of row r must not fence the loads of row r + 1 (struct members carry no restrict)
+    const int8_t* __restrict__ Ap = p.Ap;
+    int8_t* __restrict__ Awp = p.Awp;
+    const double* __restrict__ Kp = p.K;
+    const double* __restrict__ Yp = p.Y;
 #pragma unroll 2
     for (int r = 0; r < nr; r++) {
         const long long o = base + (long long)r * p.ld;
         uint32_t wa[NS];
 #pragma unroll
-        for (int pl = 0; pl < NS; pl++) wa[pl] = *reinterpret_cast<const uint32_t*>(p.Ap + (long long)pl * p.pstride + o);
-        const double4 kk = *reinterpret_cast<const double4*>(p.K + o);
-        const double4 yy = *reinterpret_cast<const double4*>(p.Y + o);
+        for (int pl = 0; pl < NS; pl++) wa[pl] = __ldg(reinterpret_cast<const uint32_t*>(Ap + (long long)pl * p.pstride + o));
+        const double4 kk = *reinterpret_cast<const double4*>(Kp + o);
+        const double4 yy = *reinterpret_cast<const double4*>(Yp + o);
         double a[4];
         planes_to_f64x4<NS>(wa, unit_a, a);
         const double k[4] = {kk.x, kk.y, kk.z, kk.w}, y[4] = {yy.x, yy.y, yy.z, yy.w};
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(128, (DT <= 4 ? 3 : 1)) kgrad_planes_kernel(co
             }
         }
 #pragma unroll
-        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(p.Awp + (long long)pl * p.pstride + o) = plane_word4<NS>(pl, lo, hi);
+        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(Awp + (long long)pl * p.pstride + o) = plane_word4<NS>(pl, lo, hi);
     }
     for (int r = nr; r < nrow; r++) {                                  // padding rows of the chunk: gv * A = 0 -> all-zero digits
 #pragma unroll

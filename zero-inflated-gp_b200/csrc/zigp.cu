@@ -115,6 +115,7 @@ struct zigp_ctx {
     //      operands (no transposed copies, no slice_cols pass, no fp64 A).
     //   0 "r1": fp64 A + planes, kgrad_kernel + slice_cols_kernel (transposed planes, per-column scales), K-major rank update.
     int oz_pipe = 1;
+    bool potrf_panel = true;       // diagonal 64-blocks of the Cholesky by the panel kernel (ZIGP_POTRF=0: the column-by-column kernel of r1)
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
     int oz_ns_grad = 0;            // mixed mode: slices used by the gradient-only contractions (Y = G A, rank update); 0 = oz_ns
     int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
@@ -271,7 +272,10 @@ int chol_inverse(zigp_ctx* c, const CholBufs& b, int tag, cudaStream_t st) {
     // blocked right-looking Cholesky
     for (int kb = 0; kb < b.nb; kb++) {
         double* diag = b.Lb + (long long)kb * NB * (Mp + 1);
-        potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, b.Dinv + (long long)kb * NB * NB, b.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, tag);
+        if (c->potrf_panel)
+            potrf_diag_panel_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, b.Dinv + (long long)kb * NB * NB, b.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, tag);
+        else
+            potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, b.Dinv + (long long)kb * NB * NB, b.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, tag);
         LAUNCHED();
         const int rem = Mp - (kb + 1) * NB;
         if (rem > 0) {
@@ -539,19 +543,22 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     const int D = c->D;
     CK(cudaMemsetAsync(c->info, 0, sizeof(int), st));
     CK(cudaMemsetAsync(c->pt_partial, 0, (size_t)c->pt_slots * 4 * sizeof(double), st));
-    for (int l = 0; l < 2; l++) {
-        Latent& L = c->lat[l];
-        CK(cudaMemsetAsync(L.E_splits, 0, (size_t)std::max(L.nsplit, L.nsplit_oz) * L.Mp * L.Mp * sizeof(double), st));
-        CK(cudaMemsetAsync(L.kg_partial, 0, (size_t)c->kg_slots * (2 + 2 * D) * L.Mp * sizeof(double), st));
-        RUN(mstage_forward(c, l, theta, st));
-    }
     // Latent f runs on the caller's stream, latent g on the context's auxiliary stream (fork / join with events around the
-    // likelihood kernel, which needs both): the tensor-core contractions of one latent overlap the fp64- and memory-bound
-    // kernels (kgen, slicing, kgrad) of the other.  Results do not depend on the interleaving (no floating-point atomics).
+    // likelihood kernel, which needs both): the tensor-core contractions of one latent overlap the fp64 / memory-bound kernels
+    // (kgen, kgrad) of the other, and the two O(M^3) M-stages -- chains of small launches that cannot fill the GPU -- run side by side.
+    // Results do not depend on the interleaving (no floating-point atomics).
     const bool two = c->engine == 1 && c->aux != nullptr && !c->profiling;     // per-kernel event timing wants the kernels alone on the GPU
     cudaStream_t sl[2] = {st, two ? c->aux : st};
     auto fork = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0)); } return 0; };
     auto join = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_join, c->aux)); CK(cudaStreamWaitEvent(st, c->ev_join, 0)); } return 0; };
+    RUN(fork());
+    for (int l = 0; l < 2; l++) {
+        Latent& L = c->lat[l];
+        CK(cudaMemsetAsync(L.E_splits, 0, (size_t)std::max(L.nsplit, L.nsplit_oz) * L.Mp * L.Mp * sizeof(double), sl[l]));
+        CK(cudaMemsetAsync(L.kg_partial, 0, (size_t)c->kg_slots * (2 + 2 * D) * L.Mp * sizeof(double), sl[l]));
+        RUN(mstage_forward(c, l, theta, sl[l]));
+    }
+    RUN(join());
     for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
         const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
         const int rows = (int)rup(nvalid, 512);
@@ -852,7 +859,9 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
         return 0;
     };
     { int r = alloc_all(); if (r) return fail(r); }
-    if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
+    if (const char* pz = getenv("ZIGP_POTRF")) c->potrf_panel = atoi(pz) != 0;
+    if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(potrf_diag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
         c->err = "cudaFuncSetAttribute(potrf_diag_kernel) failed";
         return fail(ZIGP_ECUDA);
     }
@@ -902,7 +911,9 @@ int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g
     c->chunk = rup(chunk, 512);
     const int Ms[2] = {Ms_f, Ms_g}, Mt[2] = {Mt_f, Mt_g};
     { int r = kron_alloc(c, Ms, Mt); if (r) return fail(r); }
-    if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
+    if (const char* pz = getenv("ZIGP_POTRF")) c->potrf_panel = atoi(pz) != 0;
+    if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(potrf_diag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
         c->err = "cudaFuncSetAttribute(potrf_diag_kernel) failed";
         return fail(ZIGP_ECUDA);
     }
