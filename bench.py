@@ -149,15 +149,27 @@ DENSE_ORDER = ("kernf_lengthscales", "kernf_variance", "kerng_lengthscales", "ke
                "Zf", "Zg", "u_fm", "u_gm", "u_fs_sqrt", "u_gs_sqrt")
 
 
-def parity_block(ctx, theta, out, stream, sample, order, cond=None):
+def parity_block(ctx, theta, out, stream, sample, order, cond=None, shard=None, allreduce=None):
     """evaluate the GPU path on the SAME points the CPU oracle was timed on and compare: ELBO (relative) and every gradient block (norm-wise,
-    relative to the block; blocks that are pure cancellation relative to 1e-12 of the whole gradient)"""
+    relative to the block; blocks that are pure cancellation relative to 1e-12 of the whole gradient).  With `shard` = (rank, world) every
+    rank evaluates its slice of the sample and `allreduce` sums the packed accumulator (the N > 1 data path: accumulate -> all-reduce -> finish)."""
     X, Y, (e, dt, kl, g) = sample
     Xc = np.ascontiguousarray(X, dtype=np.float64); Yc = np.ascontiguousarray(np.asarray(Y, dtype=np.float64).reshape(-1))
-    ctx.call("zigp_set_data_host", Xc.ctypes.data, Yc.ctypes.data, Xc.shape[0], 1.0, stream.cuda_stream)
-    ctx.call("zigp_elbo_grad_dev", theta.data_ptr(), out.data_ptr(), stream.cuda_stream)
+    if shard is not None:
+        rank, world = shard
+        lo, hi = Xc.shape[0] * rank // world, Xc.shape[0] * (rank + 1) // world
+        Xc, Yc = np.ascontiguousarray(Xc[lo:hi]), np.ascontiguousarray(Yc[lo:hi])
+        ctx.call("zigp_set_data_host", Xc.ctypes.data, Yc.ctypes.data, Xc.shape[0], 1.0, stream.cuda_stream)
+        ctx.call("zigp_accumulate_dev", theta.data_ptr(), stream.cuda_stream)
+        allreduce()
+        ctx.call("zigp_finish_dev", theta.data_ptr(), out.data_ptr(), stream.cuda_stream)
+    else:
+        ctx.call("zigp_set_data_host", Xc.ctypes.data, Yc.ctypes.data, Xc.shape[0], 1.0, stream.cuda_stream)
+        ctx.call("zigp_elbo_grad_dev", theta.data_ptr(), out.data_ptr(), stream.cuda_stream)
     stream.synchronize()
     o = out.cpu().numpy()
+    if shard is not None and shard[0] != 0:
+        return None
     full = np.sqrt(sum(float((g[k].numpy() ** 2).sum()) for k in order))
     pos, worst, worst_name = 4, 0.0, None
     for k in order:
@@ -170,6 +182,8 @@ def parity_block(ctx, theta, out, stream, sample, order, cond=None):
     blk = {"elbo_rel": abs(o[0] - e) / abs(e), "data_rel": abs(o[1] - dt) / abs(dt), "kl_rel": abs(o[2] - kl) / abs(kl), "grad_rel_max": worst,
            "grad_worst_block": worst_name, "points": int(Xc.shape[0]), "against": "oracle (CPU float64 restatement, pinned to the reference's source by tests/golden)",
            "info": int(o[3])}
+    if shard is not None:
+        blk["ranks"] = shard[1]; blk["path"] = "accumulate on every rank's slice of the sample -> NCCL all-reduce of the packed accumulator -> finish"
     if cond is not None:
         blk["cond_kmm"] = cond
     return blk
@@ -437,6 +451,24 @@ def run_ours(a):
         gflop = 2.0 * (4.0 * (a.ms ** 2 + a.mt ** 2) + 8.0 * a.ms * a.mt) * n_loc
         achieved = gflop / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else 0.0
 
+    # N > 1: the sharded data path (accumulate -> all-reduce -> finish) against the oracle on a small sample -- rank 0 evaluates the oracle once
+    # (untimed; the CPU baseline leg itself runs at N = 1 only), every rank evaluates its slice
+    parity_multi = None
+    if world > 1 and a.precision == "fp64" and not a.no_cpu_baseline:
+        box = [None]
+        if rank == 0:
+            if kron:
+                cpu_kron_rate(min(a.cpu_sample, 1024), a.ms, a.mt, steps=1, warmup=0); box[0] = cpu_kron_rate.last
+            else:
+                cpu_oracle_rate(a.cpu_sample, M, D, steps=1, warmup=0); box[0] = cpu_oracle_rate.last
+        dist.broadcast_object_list(box, src=0)
+
+        def _ar():
+            ptr, n = ctx.accum_buffer()
+            dist.all_reduce(m_wrap(ptr, n))
+        parity_multi = parity_block(ctx, theta, out, stream, box[0], KRON_ORDER if kron else DENSE_ORDER, shard=(rank, world), allreduce=_ar)
+        if rank == 0 and not (parity_multi["elbo_rel"] <= 1e-10 and parity_multi["grad_rel_max"] <= 1e-8 and parity_multi["info"] == 0):
+            raise SystemExit("bench.py: the sharded GPU result differs from the oracle: %r" % (parity_multi,))
     if rank == 0:
         cpu = None
         if world > 1:
@@ -451,7 +483,7 @@ def run_ours(a):
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "3 timed ELBO+grad evaluations of N_b=%d points (same generator, same M, D); median %.2f s each" % (a.cpu_sample, dt)}
         # parity on the very points the CPU leg evaluated: same parameters (seed 0), same sample, GPU through the C ABI
-        parity = None
+        parity = parity_multi
         if cpu is not None and a.precision == "fp64":
             if kron:
                 parity = parity_block(ctx, theta, out, stream, cpu_kron_rate.last, KRON_ORDER)
