@@ -101,6 +101,19 @@ int zigp_accumulate_dev(zigp_ctx* ctx, const double* theta_dev, void* stream);
 int zigp_accum_buffer(zigp_ctx* ctx, double** buf_dev, int64_t* len);
 int zigp_finish_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
 
+/* Optional C-side collective for callers without torch.distributed (zigp_comm_init; 8(e): the path's one exchange step).
+ * libnccl is loaded at run time (ZIGP_NCCL_LIB, else libnccl.so.2); contexts that never call these never touch NCCL.
+ *   zigp_comm_unique_id: rank 0 fills a 128-byte ncclUniqueId and hands it to the other ranks by its own means (file, MPI, socket ...);
+ *   zigp_comm_init:      ncclCommInitRank on the context's GPU (collective over all ranks);
+ *   zigp_comm_allreduce: in-place sum of the packed accumulator (zigp_accum_buffer) over ranks, on `stream`;
+ *   zigp_elbo_grad_dist_dev = accumulate + allreduce + finish: every rank gets the same `out`; the KL and its gradient enter once.
+ * The reference has no distributed code (single TF session, scripts/onoff.py:357). */
+int zigp_comm_unique_id(void* id128_out);
+int zigp_comm_init(zigp_ctx* ctx, const void* id128, int rank, int world);
+int zigp_comm_allreduce(zigp_ctx* ctx, void* stream);
+int zigp_elbo_grad_dist_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);
+int zigp_comm_destroy(zigp_ctx* ctx);
+
 /* KL(q(u_f)||p(u_f)) + KL(q(u_g)||p(u_g)) only (build_prior_KL / compute_prior_KL, onoffgpf/OnOffSVGP.py:73-105,164-166).
  * out_dev[0] = KL, out_dev[1] = info. */
 int zigp_prior_kl_dev(zigp_ctx* ctx, const double* theta_dev, double* out_dev, void* stream);

@@ -38,5 +38,30 @@ if rank == 0:
     for k, g in zip(orc.PARAM_NAMES, grads):
         a, b = g.cpu().numpy().reshape(-1), gf[k].numpy().reshape(-1)
         assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(b) + 1e-12 * full, k
-    print("DIST_OK world=%d elbo=%.12e" % (world, float(elbo)), flush=True)
+
+# the same evaluation through the C-side collective (zigp_comm_*: libnccl loaded by libzigp itself, no torch.distributed in the data path)
+import ctypes
+ctx = m._ctx
+idbuf = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    raw = (ctypes.c_char * 128)()
+    from onoffgpf import _cabi
+    assert _cabi.lib().zigp_comm_unique_id(ctypes.cast(raw, ctypes.c_void_p)) == 0
+    idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+idbuf = idbuf.to(dev)
+dist.broadcast(idbuf, src=0)
+raw = (ctypes.c_char * 128).from_buffer_copy(bytes(idbuf.cpu().numpy().tobytes()))
+ctx.call("zigp_comm_init", ctypes.cast(raw, ctypes.c_void_p), rank, world)
+with torch.no_grad():
+    theta = m.pack_theta().contiguous()
+out_c = torch.empty(ctx.out_len, dtype=torch.float64, device=dev)
+ctx.call("zigp_set_data_dev", m._X_dev.data_ptr(), m._Y_dev.data_ptr(), hi - lo, 1.0)       # full shard, scale = N / global batch = 1
+ctx.call("zigp_elbo_grad_dist_dev", theta.data_ptr(), out_c.data_ptr(), torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+ref_out = m._last_out
+assert abs(float(out_c[0]) - float(ref_out[0])) <= 1e-13 * abs(float(ref_out[0])), (float(out_c[0]), float(ref_out[0]))
+assert float((out_c[4:] - ref_out[4:]).norm()) <= 1e-12 * float(ref_out[4:].norm())
+ctx.call("zigp_comm_destroy")
+if rank == 0:
+    print("DIST_OK world=%d elbo=%.12e (torch.distributed and the C-side NCCL collective agree)" % (world, float(elbo)), flush=True)
 dist.destroy_process_group()

@@ -5,6 +5,7 @@
 //   -> [allreduce of the packed accumulator across ranks, done by the caller] -> M-stage backward -> packed output.
 #include <cstdio>
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -129,6 +130,8 @@ struct zigp_ctx {
     // scratch of zigp_debug_gemm (int8 engine)
     int8_t *dbg_pa = nullptr, *dbg_pb = nullptr; double *dbg_sa = nullptr, *dbg_sb = nullptr;
     size_t dbg_cap_a = 0, dbg_cap_b = 0, dbg_cap_r = 0, dbg_cap_c = 0;
+    // optional C-side collective (zigp_comm_*): an NCCL communicator created through a runtime-loaded libnccl -- no link-time dependency
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
     // Kronecker variant; nlat / lik: 2 latents + on/off likelihood (scripts/onoff.py), or the single-latent comparison models
     // 1 latent + Gaussian likelihood (scripts/svgp.py), 1 latent + probit Bernoulli (scripts/classifier.py)
     int nlat = 2, lik = 0;
@@ -923,6 +926,7 @@ int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g
 
 int zigp_destroy(zigp_ctx* c) {
     if (!c) return ZIGP_OK;
+    zigp_comm_destroy(c);
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
@@ -1176,6 +1180,99 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
     g.Out = Out; g.ldo = ldo; g.alpha = 1.0; g.beta = 0.0; g.rows = rows; g.cols = cols; g.kdim = kdim; g.tri = tri; g.stat_sq = stat_sq; g.nsplit = 1;
     CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, g, st));
     c->launches++;
+    return ZIGP_OK;
+}
+
+// ---- optional C-side collective ---------------------------------------------------------------------------------------------------
+// the path has ONE exchange step, the sum of the packed accumulator over ranks.  A torch caller does it with
+// torch.distributed (onoffgpf/parallel.py); a caller without torch uses these entry points.  libnccl is loaded at run time (dlopen of
+// ZIGP_NCCL_LIB, else libnccl.so.2 -- inside a torch process that resolves to the copy torch already loaded), so libzigp has no link-time
+// dependency on NCCL and contexts that never call zigp_comm_* never touch it.
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, char[128], int) = nullptr;     // ncclUniqueId is a 128-byte struct passed by value
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char b[128]; };
+NcclApi* nccl_api(std::string& err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[3] = {getenv("ZIGP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n) continue;
+            api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.h) break;
+        }
+        if (api.h) {
+            api.GetUniqueId = (int (*)(void*))dlsym(api.h, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, char[128], int))dlsym(api.h, "ncclCommInitRank");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.h, "ncclAllReduce");
+            api.CommDestroy = (int (*)(void*))dlsym(api.h, "ncclCommDestroy");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.h, "ncclGetErrorString");
+        }
+    }
+    if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+        err = "zigp_comm: libnccl could not be loaded (set ZIGP_NCCL_LIB to the path of libnccl.so.2)";
+        return nullptr;
+    }
+    return &api;
+}
+}  // namespace
+
+int zigp_comm_unique_id(void* id128) {
+    if (!id128) return ZIGP_EINVAL;
+    std::string err;
+    NcclApi* a = nccl_api(err);
+    if (!a) { g_create_error = err; return ZIGP_ECUDA; }
+    return a->GetUniqueId(id128) == 0 ? ZIGP_OK : ZIGP_ECUDA;
+}
+
+int zigp_comm_init(zigp_ctx* c, const void* id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return ZIGP_EINVAL;
+    if (c->nccl_comm) { c->err = "zigp_comm_init: the context already has a communicator"; return ZIGP_ESTATE; }
+    NcclApi* a = nccl_api(c->err);
+    if (!a) return ZIGP_ECUDA;
+    DeviceGuard guard(c->device);
+    typedef int (*InitFn)(void**, int, NcclId, int);
+    NcclId id;
+    memcpy(id.b, id128, 128);
+    const int r = ((InitFn)a->CommInitRank)(&c->nccl_comm, world, id, rank);
+    if (r != 0) { c->nccl_comm = nullptr; c->err = std::string("ncclCommInitRank: ") + (a->GetErrorString ? a->GetErrorString(r) : "error"); return ZIGP_ECUDA; }
+    c->comm_rank = rank; c->comm_world = world;
+    return ZIGP_OK;
+}
+
+int zigp_comm_allreduce(zigp_ctx* c, void* stream) {
+    if (!c) return ZIGP_EINVAL;
+    if (!c->nccl_comm) { c->err = "zigp_comm_allreduce: no communicator (zigp_comm_init first)"; return ZIGP_ESTATE; }
+    NcclApi* a = nccl_api(c->err);
+    if (!a) return ZIGP_ECUDA;
+    DeviceGuard guard(c->device);
+    const int r = a->AllReduce(c->accum, c->accum, (size_t)c->accum_len, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->nccl_comm, (cudaStream_t)stream);
+    if (r != 0) { c->err = std::string("ncclAllReduce: ") + (a->GetErrorString ? a->GetErrorString(r) : "error"); return ZIGP_ECUDA; }
+    return ZIGP_OK;
+}
+
+int zigp_elbo_grad_dist_dev(zigp_ctx* c, const double* theta, double* out, void* stream) {
+    if (!c || !theta || !out) return ZIGP_EINVAL;
+    RUN(do_accumulate(c, theta, (cudaStream_t)stream));
+    if (c->comm_world > 1) RUN(zigp_comm_allreduce(c, stream));
+    return do_finish(c, theta, out, (cudaStream_t)stream);
+}
+
+int zigp_comm_destroy(zigp_ctx* c) {
+    if (!c) return ZIGP_EINVAL;
+    if (c->nccl_comm) {
+        std::string err;
+        if (NcclApi* a = nccl_api(err)) { DeviceGuard guard(c->device); cudaDeviceSynchronize(); a->CommDestroy(c->nccl_comm); }
+        c->nccl_comm = nullptr; c->comm_world = 1; c->comm_rank = 0;
+    }
     return ZIGP_OK;
 }
 

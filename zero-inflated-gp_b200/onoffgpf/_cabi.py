@@ -29,6 +29,11 @@ SYMBOLS = {
     "zigp_accumulate_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "zigp_accum_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "zigp_finish_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "zigp_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "zigp_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "zigp_elbo_grad_dist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zigp_comm_destroy": (C.c_int, [C.c_void_p]),
     "zigp_prior_kl_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zigp_predict_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "zigp_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
