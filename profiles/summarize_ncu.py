@@ -6,7 +6,9 @@ import csv
 import subprocess
 import sys
 
-KEYS = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg",
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.sum.per_second", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__cluster_dim_x", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg",
         "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",

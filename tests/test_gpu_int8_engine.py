@@ -95,6 +95,29 @@ def test_planes_pipeline_equals_the_r1_pipeline(monkeypatch):
         assert np.linalg.norm(ga[k] - gb[k]) <= 1e-10 * np.linalg.norm(gb[k]) + 1e-13 * full, (k, np.linalg.norm(ga[k] - gb[k]) / np.linalg.norm(gb[k]))
 
 
+def test_mma_glue_schedule_is_bit_identical_to_the_per_latent_schedule(monkeypatch):
+    """ZIGP_OZ_SCHED=1 (contractions of both latents on one stream, Kmn tiles / likelihood / gradient sums on the other, tied by events) only
+    changes WHEN kernels run: the packed result must be bit-identical to ZIGP_OZ_SCHED=0 (one stream per latent), on a ragged five-chunk problem,
+    twice in a row (a missing dependency shows up as a changed or irreproducible result)"""
+    N, M, D = 300_001, 256, 3
+    X, Y = synth.make_data(N, D, 23)
+    p = synth.make_params(M, M, D, 23)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZIGP_OZ_SCHED", mode)
+        m = synth.build_model(X, Y, p, engine="int8", chunk_rows=65536)
+        seq = []
+        for _ in range(3):
+            m.build_likelihood()
+            seq.append(m._last_out.cpu().numpy().copy())
+        outs[mode] = seq
+        del m
+        torch.cuda.empty_cache()
+    for a in outs["1"][1:]:
+        assert np.array_equal(a, outs["1"][0])
+    assert np.array_equal(outs["1"][0], outs["0"][0])
+
+
 def test_engines_agree_at_scale():
     """the two engines on the same 200 000-point problem: ELBO to 1e-12, every gradient block to 1e-10 of its norm"""
     N, M, D = 200_000, 256, 3

@@ -329,8 +329,11 @@ __global__ void __launch_bounds__(256) slice_fixed_kernel(const double* __restri
 // per column into this CTA's slot (as kgrad_kernel, nstage.cuh), and WRITES the digit planes of gv_n A[n, m] -- point-major, [p][n][m] --
 // under ONE power-of-two scale 2^e > 4 sqrt(var) max_n |gv_n| (|A_nm| <= sqrt(var); the maximum comes from the likelihood kernel).  The rank
 // update E += (gv A)^T A then contracts those planes with A's own planes as MN-major operands: no transposed copies, no separate slicing pass.
-// Thread = 4 consecutive columns (4-byte plane words, 32-byte fp64 loads), warp = 128 columns, CTA = 512 columns x KGP_ROWS rows.
+// Thread = 4 consecutive columns (4-byte plane words, 32-byte fp64 loads), warp = 128 columns, CTA = 2 warps = 256 columns x KGP_ROWS rows:
+// 64 threads x 168 registers fit beside a persistent contraction CTA (which leaves 11.7K registers and 56 KB of shared memory per SM), so the
+// kernel can run on the second stream UNDER the tensor-core kernels of the other latent; alone it still reaches 6 CTAs = 12 warps per SM.
 constexpr int KGP_ROWS = 128;
+constexpr int KGP_THREADS = 64;
 struct KgradPArgs {
     const double* K; const double* Y; long long ld;
     const int8_t* Ap; int8_t* Awp; long long pstride;          // planes of A (in) and of gv * A (out), plane stride in bytes
@@ -344,15 +347,15 @@ struct KgradPArgs {
 };
 
 template <int NS, int DT>
-__global__ void __launch_bounds__(128, (DT <= 4 ? 3 : 1)) kgrad_planes_kernel(const KgradPArgs p) {
+__global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? 6 : 1)) kgrad_planes_kernel(const KgradPArgs p) {
     __shared__ double sx[KGP_ROWS][DT];
     __shared__ double sgm[KGP_ROWS], sgv[KGP_ROWS];
-    const int m0 = blockIdx.x * 512 + threadIdx.x * 4;
+    const int m0 = blockIdx.x * (KGP_THREADS * 4) + threadIdx.x * 4;
     const int r0 = blockIdx.y * KGP_ROWS;
     const int nr = max(0, min(KGP_ROWS, p.nvalid - r0));
     const int nrow = min(KGP_ROWS, p.rows - r0);                       // rows of this block inside the padded chunk
-    for (int e = threadIdx.x; e < nr * p.D; e += 128) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
-    for (int e = threadIdx.x; e < nr; e += 128) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
+    for (int e = threadIdx.x; e < nr * p.D; e += KGP_THREADS) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
+    for (int e = threadIdx.x; e < nr; e += KGP_THREADS) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
     __syncthreads();
     if (m0 >= p.Mp) return;
     const double sd = sqrt(p.var[0]);
@@ -427,8 +430,8 @@ __global__ void __launch_bounds__(128, (DT <= 4 ? 3 : 1)) kgrad_planes_kernel(co
 }
 
 inline cudaError_t launch_kgrad_planes(int ns, const KgradPArgs& k, cudaStream_t st) {
-    const dim3 grid((k.Mp + 511) / 512, (k.rows + KGP_ROWS - 1) / KGP_ROWS);
-#define ZIGP_KGP(NSV, DTV) kgrad_planes_kernel<NSV, DTV><<<grid, 128, 0, st>>>(k)
+    const dim3 grid((k.Mp + KGP_THREADS * 4 - 1) / (KGP_THREADS * 4), (k.rows + KGP_ROWS - 1) / KGP_ROWS);
+#define ZIGP_KGP(NSV, DTV) kgrad_planes_kernel<NSV, DTV><<<grid, KGP_THREADS, 0, st>>>(k)
 #define ZIGP_KGP_D(NSV)                                  \
     switch (k.D) {                                       \
         case 1: ZIGP_KGP(NSV, 1); break;                 \

@@ -116,6 +116,13 @@ struct zigp_ctx {
     //      operands (no transposed copies, no slice_cols pass, no fp64 A).
     //   0 "r1": fp64 A + planes, kgrad_kernel + slice_cols_kernel (transposed planes, per-column scales), K-major rank update.
     int oz_pipe = 1;
+    // Schedule of the two streams (ZIGP_OZ_SCHED, planes pipeline only):
+    //   1 (default) "mma / glue": ALL tensor-core contractions of both latents run in order on the caller's stream, the fp64- and memory-bound
+    //      kernels (Kmn tiles, likelihood, gradient sums) on the auxiliary stream, tied by events on the buffers they exchange; the glue of one
+    //      latent then runs under the contractions of the other (kgen(g) under A/RA/Y(f), kgrad(g) and the next chunk's kgen under the rank updates).
+    //   0 "per latent": latent f on the caller's stream, latent g on the auxiliary one, joined around the likelihood kernel (r1).
+    int oz_sched = 1;
+    std::vector<cudaEvent_t> evpool; size_t evnext = 0;
     bool potrf_panel = true;       // diagonal 64-blocks of the Cholesky by the panel kernel (ZIGP_POTRF=0: the column-by-column kernel of r1)
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
     int oz_ns_grad = 0;            // mixed mode: slices used by the gradient-only contractions (Y = G A, rank update); 0 = oz_ns
@@ -401,27 +408,36 @@ int oz_slice_A(zigp_ctx* c, Latent& L, int rows, int Mp, cudaStream_t st) {
     return 0;
 }
 
+// int8 engine, the two halves of a chunk's forward for one latent (separate so that the mma / glue schedule can put them on different streams):
+// Kmn tiles and their digit planes in one kernel (fixed row scale 2^e > 4 var: no max pass, no separate slicing launch) ...
+int chunk_kgen(zigp_ctx* c, int l, const double* theta, const double* X, long long n0, int nvalid, int rows, cudaStream_t st) {
+    Latent& L = c->lat[l];
+    ProfScope ps(c, PC_KGEN, st);
+    CK(oz::launch_kgen_sliced(c->oz_ns, X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, L.Mp, L.Kb, L.oz_in,
+                              (long long)rows * L.Mp, L.oz_rs, st));
+    c->launches++;
+    return 0;
+}
+// ... and the contractions A = K T^T (+ |A|^2, A.alpha_w; the epilogue re-slices A for the next products), |R A|^2, Y = G A
+int chunk_products(zigp_ctx* c, int l, const double* theta, int rows, bool need_bwd, cudaStream_t st) {
+    Latent& L = c->lat[l];
+    const int fuse = c->oz_pipe ? 1 : (c->oz_fuse >= 2 && !need_bwd ? 1 : c->oz_fuse);
+    // planes pipeline: no fp64 A at all -- its only readers were the gradient kernel and the transposed slicer
+    RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, c->oz_pipe ? nullptr : L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
+    if (!fuse) RUN(oz_slice_A(c, L, rows, L.Mp, st));
+    RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
+    if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));
+    return 0;
+}
+
 // forward contractions of one chunk for one latent: K, A (+stats), RA (+stats); optionally V, Y for the backward
 int chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long long n0, int nvalid, int rows, bool need_bwd, cudaStream_t st) {
     Latent& L = c->lat[l];
     const int Mp = L.Mp;
     dim3 gk(Mp / 32, rows / 64);
     if (c->engine == 1 && rows % oz::OBM == 0) {
-        {
-            // Kmn tiles and their digit planes in one kernel (fixed row scale 2^e > 4 var: no max pass, no separate slicing launch)
-            ProfScope ps(c, PC_KGEN, st);
-            CK(oz::launch_kgen_sliced(c->oz_ns, X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, Mp, L.Kb, L.oz_in,
-                                      (long long)rows * Mp, L.oz_rs, st));
-            c->launches++;
-        }
-        // A = K T^T, |A|^2, A.alpha_w; the epilogue re-slices A for the next products (and, oz_fuse == 2, for the rank update)
-        const int fuse = c->oz_pipe ? 1 : (c->oz_fuse >= 2 && !need_bwd ? 1 : c->oz_fuse);
-        // planes pipeline: no fp64 A at all -- its only readers were the gradient kernel and the transposed slicer
-        RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, c->oz_pipe ? nullptr : L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
-        if (!fuse) RUN(oz_slice_A(c, L, rows, Mp, st));
-        RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
-        if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));
-        return 0;
+        RUN(chunk_kgen(c, l, theta, X, n0, nvalid, rows, st));
+        return chunk_products(c, l, theta, rows, need_bwd, st);
     }
     {
         ProfScope ps(c, PC_KGEN, st);
@@ -472,32 +488,41 @@ int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long lon
 }
 
 // backward of one chunk for one latent: Kmn-side gradient sums and the whitened rank update E += A^T diag(gv) A
+// planes pipeline, the two halves of a chunk's backward for one latent.  chunk_kgrad: one pass over K, Y and A's digit planes -> gradient sums
+// + digit planes of gv * A (point-major) ...
+int chunk_kgrad(zigp_ctx* c, int l, const double* theta, long long n0, int nvalid, int rows, cudaStream_t st) {
+    Latent& L = c->lat[l];
+    oz::KgradPArgs k{};
+    k.K = L.Kb; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = (long long)rows * L.Mp;
+    k.gm = L.gm; k.gv = L.gv; k.beta = L.beta; k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows;
+    k.Z = theta + L.off_Z; k.M = L.M; k.D = c->D; k.Mp = L.Mp; k.var = theta + L.off_var; k.gvmax = L.oz_gvmax;
+    k.partial = L.kg_partial; k.a_scale = L.oz_csA; k.aw_scale = L.oz_csAw;
+    ProfScope ps(c, PC_KGRAD, st);
+    CK(oz::launch_kgrad_planes(c->oz_ns, k, st));
+    c->launches++;
+    return 0;
+}
+// ... chunk_rank: the rank update E += (gv A)^T A straight from the two point-major plane sets (MN-major operands, k = point index)
+int chunk_rank(zigp_ctx* c, int l, int rows, cudaStream_t st) {
+    Latent& L = c->lat[l];
+    const long long pstride = (long long)rows * L.Mp;
+    oz::OzOperand A{L.oz_colAw, rows, L.Mp, pstride, L.oz_csAw, true, L.Mp};
+    oz::OzOperand B{L.oz_inA, rows, L.Mp, pstride, L.oz_csA, true, L.Mp};
+    oz::OzArgs a{};
+    a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
+    a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
+    ProfScope ps(c, PC_SYRK, st);
+    CK(oz::launch_ozaki_gemm((c->oz_ns_grad && c->oz_ns == oz::NS64) ? c->oz_ns_grad : c->oz_ns, A, B, a, st));
+    c->launches++;
+    return 0;
+}
+
 int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nvalid, int rows, cudaStream_t st) {
     const int D = c->D;
     Latent& L = c->lat[l];
     if (c->engine == 1 && c->oz_pipe && rows % oz::OBM == 0) {
-        // planes pipeline: one pass over K, Y and A's digit planes -> gradient sums + digit planes of gv * A (point-major), then the rank
-        // update E += (gv A)^T A straight from the two point-major plane sets (MN-major operands, k = point index)
-        const long long pstride = (long long)rows * L.Mp;
-        oz::KgradPArgs k{};
-        k.K = L.Kb; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = pstride;
-        k.gm = L.gm; k.gv = L.gv; k.beta = L.beta; k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows;
-        k.Z = theta + L.off_Z; k.M = L.M; k.D = D; k.Mp = L.Mp; k.var = theta + L.off_var; k.gvmax = L.oz_gvmax;
-        k.partial = L.kg_partial; k.a_scale = L.oz_csA; k.aw_scale = L.oz_csAw;
-        {
-            ProfScope ps(c, PC_KGRAD, st);
-            CK(oz::launch_kgrad_planes(c->oz_ns, k, st));
-            c->launches++;
-        }
-        oz::OzOperand A{L.oz_colAw, rows, L.Mp, pstride, L.oz_csAw, true, L.Mp};
-        oz::OzOperand B{L.oz_inA, rows, L.Mp, pstride, L.oz_csA, true, L.Mp};
-        oz::OzArgs a{};
-        a.Out = L.E_splits; a.ldo = L.Mp; a.Zin = L.E_splits; a.ldz = L.Mp; a.alpha = 1.0; a.beta = 1.0; a.rows = L.Mp; a.cols = L.Mp; a.kdim = rows;
-        a.tri = TRI_FULL; a.lower_only = 1; a.nsplit = L.nsplit_oz; a.split_stride = (long long)L.Mp * L.Mp;
-        ProfScope ps(c, PC_SYRK, st);
-        CK(oz::launch_ozaki_gemm((c->oz_ns_grad && c->oz_ns == oz::NS64) ? c->oz_ns_grad : c->oz_ns, A, B, a, st));
-        c->launches++;
-        return 0;
+        RUN(chunk_kgrad(c, l, theta, n0, nvalid, rows, st));
+        return chunk_rank(c, l, rows, st);
     }
     KgradArgs k{};
     k.K = L.Kb; k.Y = L.RAb; k.A = L.Ab; k.ld = L.Mp; k.gm = L.gm; k.gv = L.gv; k.beta = L.beta;
@@ -562,6 +587,39 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
         RUN(mstage_forward(c, l, theta, sl[l]));
     }
     RUN(join());
+    if (two && c->oz_pipe && c->oz_sched == 1) {
+        // mma / glue schedule.  M = st (contractions), G = aux (everything else).  edge(a, b): work recorded so far on a precedes later work on b.
+        cudaStream_t Ms = st, Gs = c->aux;
+        c->evnext = 0;
+        auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {
+            if (c->evnext == c->evpool.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->evpool.push_back(e); }
+            cudaEvent_t e = c->evpool[c->evnext++];
+            CK(cudaEventRecord(e, from)); CK(cudaStreamWaitEvent(to, e, 0));
+            return 0;
+        };
+        RUN(edge(Ms, Gs));                                  // the M-stage (both latents, joined into st above) precedes everything
+        for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
+            const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
+            const int rows = (int)rup(nvalid, 512);
+            if (rows % oz::OBM != 0) { c->err = "internal: chunk rows not a multiple of the tile"; return ZIGP_EINVAL; }
+            for (int l = 0; l < 2; l++) {
+                // G: Kmn tile + planes of latent l (its previous readers -- A(c-1, l) on M, kgrad(c-1, l) on G -- are complete: kgrad(c-1, l)
+                // waited for Y(c-1, .) on M, which follows A(c-1, l) there, and G is in order)
+                RUN(chunk_kgen(c, l, theta, c->X, n0, nvalid, rows, Gs));
+                RUN(edge(Gs, Ms));
+                // M: A = K T^T, |R A|^2, Y = G A of latent l
+                RUN(chunk_products(c, l, theta, rows, true, Ms));
+            }
+            RUN(edge(Ms, Gs));                              // both forwards done -> likelihood
+            RUN(run_point_kernel(c, theta, c->Y, n0, nvalid, rows, Gs));
+            for (int l = 0; l < 2; l++) {
+                RUN(chunk_kgrad(c, l, theta, n0, nvalid, rows, Gs));
+                RUN(edge(Gs, Ms));
+                RUN(chunk_rank(c, l, rows, Ms));
+            }
+        }
+        RUN(edge(Gs, Ms));
+    } else
     for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
         const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
         const int rows = (int)rup(nvalid, 512);
@@ -871,6 +929,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     // default engine: fp64 on the int8 tensor cores; ZIGP_ENGINE=dmma (or zigp_set_engine(ctx, 0)) selects the DMMA engine
     if (const char* fz = getenv("ZIGP_OZ_FUSE")) c->oz_fuse = atoi(fz);
     if (const char* pz = getenv("ZIGP_OZ_PIPE")) c->oz_pipe = atoi(pz) != 0;
+    if (const char* sz = getenv("ZIGP_OZ_SCHED")) c->oz_sched = atoi(sz);
     const char* env = getenv("ZIGP_ENGINE");
     if (!(env && std::string(env) == "dmma")) {
         // no silent downgrade: a context that cannot set up its default engine fails to create (ZIGP_ENGINE=dmma asks for the DMMA engine)
@@ -939,6 +998,7 @@ int zigp_destroy(zigp_ctx* c) {
     if (c->cap) cudaStreamDestroy(c->cap);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (cudaEvent_t e : c->evpool) cudaEventDestroy(e);
     if (c->theta_pin) cudaFreeHost(c->theta_pin);
     if (c->out_pin) cudaFreeHost(c->out_pin);
     delete c;
@@ -1011,7 +1071,7 @@ int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if (c->graph_on && !c->profiling && c->has_data) {
         DeviceGuard guard(c->device);
-        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad + 256 * c->oz_pipe};
+        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad + 256 * c->oz_pipe + 512 * c->oz_sched};
         if (!c->gexec || memcmp(&key, &c->gkey, sizeof key) != 0) {
             // (re)capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
             if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
