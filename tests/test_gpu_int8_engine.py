@@ -95,15 +95,16 @@ def test_planes_pipeline_equals_the_r1_pipeline(monkeypatch):
         assert np.linalg.norm(ga[k] - gb[k]) <= 1e-10 * np.linalg.norm(gb[k]) + 1e-13 * full, (k, np.linalg.norm(ga[k] - gb[k]) / np.linalg.norm(gb[k]))
 
 
-def test_mma_glue_schedule_is_bit_identical_to_the_per_latent_schedule(monkeypatch):
-    """ZIGP_OZ_SCHED=1 (contractions of both latents on one stream, Kmn tiles / likelihood / gradient sums on the other, tied by events) only
-    changes WHEN kernels run: the packed result must be bit-identical to ZIGP_OZ_SCHED=0 (one stream per latent), on a ragged five-chunk problem,
-    twice in a row (a missing dependency shows up as a changed or irreproducible result)"""
+def test_stream_schedules_are_bit_identical(monkeypatch):
+    """ZIGP_OZ_SCHED=2 (default: chunk-pipelined -- contractions on a high-priority stream, Kmn tiles / likelihood / gradient sums on a second
+    stream one chunk ahead / behind, doubled hand-over buffers, event edges) and =1 (same two roles without the doubling) only change WHEN kernels
+    run: the packed result must be bit-identical to ZIGP_OZ_SCHED=0 (one stream per latent), on a ragged five-chunk problem, three times in a row
+    (a missing dependency shows up as a changed or irreproducible result)"""
     N, M, D = 300_001, 256, 3
     X, Y = synth.make_data(N, D, 23)
     p = synth.make_params(M, M, D, 23)
     outs = {}
-    for mode in ("0", "1"):
+    for mode in ("0", "1", "2"):
         monkeypatch.setenv("ZIGP_OZ_SCHED", mode)
         m = synth.build_model(X, Y, p, engine="int8", chunk_rows=65536)
         seq = []
@@ -113,9 +114,19 @@ def test_mma_glue_schedule_is_bit_identical_to_the_per_latent_schedule(monkeypat
         outs[mode] = seq
         del m
         torch.cuda.empty_cache()
-    for a in outs["1"][1:]:
-        assert np.array_equal(a, outs["1"][0])
-    assert np.array_equal(outs["1"][0], outs["0"][0])
+    for mode in ("1", "2"):
+        for a in outs[mode]:
+            assert np.array_equal(a, outs["0"][0]), mode
+    # one chunk and two chunks (prologue / epilogue of the pipeline), with graph replay as the mirrors use it for small batches
+    for n in (3000, 70_000):
+        res = {}
+        for mode in ("0", "2"):
+            monkeypatch.setenv("ZIGP_OZ_SCHED", mode)
+            m = synth.build_model(X[:n], Y[:n], p, engine="int8", chunk_rows=65536)
+            m.build_likelihood(); m.build_likelihood()
+            res[mode] = m._last_out.cpu().numpy().copy()
+            del m
+        assert np.array_equal(res["0"], res["2"]), n
 
 
 def test_engines_agree_at_scale():

@@ -117,16 +117,19 @@ __global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restric
         const int c0 = pk * PB;
         if (warp == 0) {
             const int i = lane & (PB - 1);          // lanes 16..31 mirror lanes 0..15, so every shuffle is a full-warp shuffle
-            double a[PB];
+            double a[PB], rd[PB];                    // rd[j] = 1 / L_jj: one rsqrt per pivot, no division anywhere (the serial chain of this
+                                                     // warp is the critical path of the whole M-stage: 64 dependent pivots per 64-block)
 #pragma unroll
             for (int j = 0; j < PB; j++) a[j] = L[c0 + i][c0 + j];
 #pragma unroll
             for (int j = 0; j < PB; j++) {
                 const double djj = __shfl_sync(0xffffffffu, a[j], j);
                 if (!(djj > 0.0) && lane == 0) atomicCAS(info, 0, (latent << 20) + pivot_base + c0 + j + 1);
-                const double d = sqrt(djj);
-                if (i == j) a[j] = d;
-                else if (i > j) a[j] = a[j] / d;
+                double r = rsqrt(djj);
+                r = r * fma(-0.5 * djj * r, r, 1.5);   // one Newton step on 1/sqrt: the result is within an ulp of the correctly rounded value
+                rd[j] = r;
+                if (i == j) a[j] = djj * r;            // sqrt(d) = d / sqrt(d)
+                else if (i > j) a[j] = a[j] * r;
 #pragma unroll
                 for (int k = j + 1; k < PB; k++) {
                     const double lkj = __shfl_sync(0xffffffffu, a[j], k);
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(256) potrf_diag_panel_kernel(double* __restric
                     double sacc = (r == c) ? 1.0 : 0.0;
 #pragma unroll
                     for (int k = 0; k < r; k++) sacc = fma(-L[c0 + r][c0 + k], x[k], sacc);
-                    x[r] = sacc / L[c0 + r][c0 + r];
+                    x[r] = sacc * rd[r];
                 }
 #pragma unroll
                 for (int r = 0; r < PB; r++) { Di[r][c] = x[r]; X[c0 + r][c0 + c] = x[r]; }

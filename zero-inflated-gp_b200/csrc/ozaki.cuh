@@ -334,6 +334,13 @@ __global__ void __launch_bounds__(256) slice_fixed_kernel(const double* __restri
 // kernel can run on the second stream UNDER the tensor-core kernels of the other latent; alone it still reaches 6 CTAs = 12 warps per SM.
 constexpr int KGP_ROWS = 128;
 constexpr int KGP_THREADS = 64;
+#ifndef ZIGP_KGP_MINB
+#define ZIGP_KGP_MINB 6
+#endif
+#ifndef ZIGP_KGP_UNROLL
+#define ZIGP_KGP_UNROLL 2
+#endif
+constexpr int KGP_UNROLL = ZIGP_KGP_UNROLL;
 struct KgradPArgs {
     const double* K; const double* Y; long long ld;
     const int8_t* Ap; int8_t* Awp; long long pstride;          // planes of A (in) and of gv * A (out), plane stride in bytes
@@ -347,7 +354,7 @@ struct KgradPArgs {
 };
 
 template <int NS, int DT>
-__global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? 6 : 1)) kgrad_planes_kernel(const KgradPArgs p) {
+__global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kgrad_planes_kernel(const KgradPArgs p) {
     __shared__ double sx[KGP_ROWS][DT];
     __shared__ double sgm[KGP_ROWS], sgv[KGP_ROWS];
     const int m0 = blockIdx.x * (KGP_THREADS * 4) + threadIdx.x * 4;
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? 6 : 1)) kgrad_planes_k
     int8_t* __restrict__ Awp = p.Awp;
     const double* __restrict__ Kp = p.K;
     const double* __restrict__ Yp = p.Y;
-#pragma unroll 2
+#pragma unroll KGP_UNROLL
     for (int r = 0; r < nr; r++) {
         const long long o = base + (long long)r * p.ld;
         uint32_t wa[NS];

@@ -50,6 +50,11 @@ struct Latent {
     double *oz_rs = nullptr, *oz_rsA = nullptr, *oz_csA = nullptr, *oz_csAw = nullptr;
     unsigned long long* oz_colmax = nullptr;
     unsigned long long* oz_gvmax = nullptr;       // planes pipeline: max_n |gv_n| of the current chunk (bit pattern), from the likelihood kernel
+    // chunk-pipelined schedule (ZIGP_OZ_SCHED=2): the buffers a chunk hands from its forward to its backward exist twice, so that the backward
+    // glue of chunk c (gradient sums) runs under the forward contractions of chunk c + 1.  [0] = the buffers above.
+    double *Kb2[2] = {nullptr, nullptr}, *RAb2[2] = {nullptr, nullptr}, *gm2[2] = {nullptr, nullptr}, *gv2[2] = {nullptr, nullptr};
+    int8_t* inA2[2] = {nullptr, nullptr};
+    unsigned long long* gvmax2[2] = {nullptr, nullptr};
     int nsplit_oz = 4;
 };
 
@@ -116,12 +121,17 @@ struct zigp_ctx {
     //      operands (no transposed copies, no slice_cols pass, no fp64 A).
     //   0 "r1": fp64 A + planes, kgrad_kernel + slice_cols_kernel (transposed planes, per-column scales), K-major rank update.
     int oz_pipe = 1;
-    // Schedule of the two streams (ZIGP_OZ_SCHED, planes pipeline only):
-    //   1 (default) "mma / glue": ALL tensor-core contractions of both latents run in order on the caller's stream, the fp64- and memory-bound
+    // Schedule of the streams (ZIGP_OZ_SCHED, planes pipeline only).  All three give bit-identical results and, measured, the same step time
+    // (N = 2^22: 574.2 / 584.7 / 574.3 ms for 0 / 1 / 2): the contractions pull ~11 TB/s from L2 through TMA, so a memory-bound kernel running
+    // beside them slows them by what it gains (class times with both streams live: contractions 411 -> 457 ms with the gradient kernel underneath);
+    // only the ALU-bound Kmn kernel overlaps for free.  0 stays the default (least memory, simplest); 1 and 2 are kept as measured alternatives.
+    //   2 "chunk-pipelined": as 1, on a highest-priority contraction stream, and with the forward -> backward hand-over buffers doubled so that
+    //      the gradient sums of chunk c and the Kmn tiles of chunk c + 2 run under the contractions of chunk c + 1 (accumulate_pipelined).
+    //   1 "mma / glue": ALL tensor-core contractions of both latents run in order on the caller's stream, the fp64- and memory-bound
     //      kernels (Kmn tiles, likelihood, gradient sums) on the auxiliary stream, tied by events on the buffers they exchange; the glue of one
     //      latent then runs under the contractions of the other (kgen(g) under A/RA/Y(f), kgrad(g) and the next chunk's kgen under the rank updates).
-    //   0 "per latent": latent f on the caller's stream, latent g on the auxiliary one, joined around the likelihood kernel (r1).
-    int oz_sched = 1;
+    //   0 (default) "per latent": latent f on the caller's stream, latent g on the auxiliary one, joined around the likelihood kernel (r1).
+    int oz_sched = 0;
     std::vector<cudaEvent_t> evpool; size_t evnext = 0;
     bool potrf_panel = true;       // diagonal 64-blocks of the Cholesky by the panel kernel (ZIGP_POTRF=0: the column-by-column kernel of r1)
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
@@ -129,6 +139,8 @@ struct zigp_ctx {
     int oz_ns = oz::NS64;          // slices per operand: 7 = fp64 precision, 4 = fp32-class precision (zigp_set_precision)
     // second stream for latent g (the int8 contractions of one latent overlap the fp64 / memory-bound kernels of the other)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t hi = nullptr;        // highest-priority stream: the tensor-core contractions of the mma / glue schedule (its CTAs are placed first,
+                                      // the glue kernels of the other stream fill whatever registers and shared memory remain on each SM)
     // CUDA-graph replay of one whole evaluation (zigp_set_graph): the launch sequence of zigp_elbo_grad_dev depends only on the pointers and
     // sizes below, so it is captured once on `cap` and replayed -- a minibatch step of the reference's size is launch-bound (~150 kernels)
     bool graph_on = false;
@@ -419,14 +431,16 @@ int chunk_kgen(zigp_ctx* c, int l, const double* theta, const double* X, long lo
     return 0;
 }
 // ... and the contractions A = K T^T (+ |A|^2, A.alpha_w; the epilogue re-slices A for the next products), |R A|^2, Y = G A
-int chunk_products(zigp_ctx* c, int l, const double* theta, int rows, bool need_bwd, cudaStream_t st) {
+int chunk_products(zigp_ctx* c, int l, const double* theta, int rows, bool need_bwd, cudaStream_t st, int which = 3) {
     Latent& L = c->lat[l];
     const int fuse = c->oz_pipe ? 1 : (c->oz_fuse >= 2 && !need_bwd ? 1 : c->oz_fuse);
-    // planes pipeline: no fp64 A at all -- its only readers were the gradient kernel and the transposed slicer
-    RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, c->oz_pipe ? nullptr : L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
-    if (!fuse) RUN(oz_slice_A(c, L, rows, L.Mp, st));
-    RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
-    if (need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));
+    if (which & 1) {
+        // planes pipeline: no fp64 A at all -- its only readers were the gradient kernel and the transposed slicer
+        RUN(oz_product(c, L, 0, false, rows, TRI_LOWER, c->oz_pipe ? nullptr : L.Ab, L.sqA, L.dotA, L.aw, fuse, theta + L.off_var, st));
+        if (!fuse) RUN(oz_slice_A(c, L, rows, L.Mp, st));
+        RUN(oz_product(c, L, 1, true, rows, TRI_UPPER, nullptr, L.sqRA, nullptr, nullptr, 0, nullptr, st));       // |R A|^2 only: RA is never stored
+    }
+    if ((which & 2) && need_bwd) RUN(oz_product(c, L, 2, true, rows, TRI_FULL, L.RAb, nullptr, nullptr, nullptr, 0, nullptr, st));
     return 0;
 }
 
@@ -565,6 +579,104 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
     return 0;
 }
 
+// Chunk-pipelined schedule of the planes pipeline (ZIGP_OZ_SCHED=2).  M = highest-priority stream: every tensor-core contraction, in the order
+//     A RA Y (c, f)   A RA Y (c, g)   rank (c-1, f)   rank (c-1, g)   A RA Y (c+1, f) ...
+// G = auxiliary stream (default priority): everything else, in the order (while M works on chunk c)
+//     kgrad (c-1, f)   kgrad (c-1, g)   kgen (c+1, f)   kgen (c+1, g)   likelihood (c)
+// M's CTAs are placed first; G's kernels run in the registers / shared memory M's persistent CTAs leave free (one small CTA per SM) and at
+// full speed whenever M waits.  The buffers a chunk hands from forward to backward (K, A's planes, Y, gm / gv, max|gv|) alternate between two
+// copies; every other hazard is an explicit event edge.  The arithmetic and every accumulation order are those of the other schedules: results
+// are bit-identical (tests/test_gpu_int8_engine.py).
+int accumulate_pipelined(zigp_ctx* c, const double* theta, cudaStream_t st) {
+    cudaStream_t Ms = c->hi ? c->hi : st, Gs = c->aux;
+    c->evnext = 0;
+    auto record = [&](cudaStream_t on, cudaEvent_t* out) -> int {
+        if (c->evnext == c->evpool.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->evpool.push_back(e); }
+        *out = c->evpool[c->evnext++];
+        CK(cudaEventRecord(*out, on));
+        return 0;
+    };
+    auto wait = [&](cudaStream_t s, cudaEvent_t e) -> int { if (e) CK(cudaStreamWaitEvent(s, e, 0)); return 0; };
+    auto use = [&](int l, int b) {            // point latent l's hand-over buffers at copy b (the launch helpers read them at launch time)
+        Latent& L = c->lat[l];
+        L.Kb = L.Kb2[b]; L.RAb = L.RAb2[b]; L.gm = L.gm2[b]; L.gv = L.gv2[b]; L.oz_inA = L.inA2[b]; L.oz_gvmax = L.gvmax2[b];
+    };
+    const long long chunk = c->chunk;
+    const int nchunks = (int)((c->n_local + chunk - 1) / chunk);
+    auto geom = [&](int ci, long long& n0, int& nvalid, int& rows) {
+        n0 = (long long)ci * chunk; nvalid = (int)std::min<long long>(chunk, c->n_local - n0); rows = (int)rup(nvalid, 512);
+    };
+    cudaEvent_t e0 = nullptr;
+    RUN(record(st, &e0));                      // the M-stage (joined into st by the caller) precedes everything on both streams
+    if (Ms != st) RUN(wait(Ms, e0));
+    RUN(wait(Gs, e0));
+    cudaEvent_t e_kgen[2] = {nullptr, nullptr}, e_A[2] = {nullptr, nullptr}, e_Y[2] = {nullptr, nullptr}, e_kgrad[2] = {nullptr, nullptr},
+                e_rank[2] = {nullptr, nullptr}, e_stats = nullptr, e_point = nullptr;
+    long long n0; int nvalid, rows;
+    // prologue: Kmn tiles of chunk 0
+    geom(0, n0, nvalid, rows);
+    for (int l = 0; l < 2; l++) { use(l, 0); RUN(chunk_kgen(c, l, theta, c->X, n0, nvalid, rows, Gs)); RUN(record(Gs, &e_kgen[l])); }
+    for (int ci = 0; ci <= nchunks; ci++) {
+        const int b = ci & 1;
+        if (ci < nchunks) {
+            // ---- M: forward contractions of chunk ci
+            geom(ci, n0, nvalid, rows);
+            for (int l = 0; l < 2; l++) {
+                use(l, b);
+                RUN(wait(Ms, e_kgen[l]));                          // K planes of (ci, l)
+                if (l == 0) RUN(wait(Ms, e_point));                // the row statistics of chunk ci - 1 have been consumed by its likelihood kernel
+                RUN(chunk_products(c, l, theta, rows, true, Ms, 1));   // A (+ planes, statistics), |R A|^2
+                RUN(record(Ms, &e_A[l]));                          // oz_in (K planes) of latent l is free again; statistics of l are ready
+                if (l == 1) RUN(record(Ms, &e_stats));
+                RUN(chunk_products(c, l, theta, rows, true, Ms, 2));   // Y = G A
+                RUN(record(Ms, &e_Y[l]));
+            }
+        }
+        if (ci > 0) {
+            // ---- G: gradient sums of chunk ci - 1 (under the contractions of chunk ci); M: its rank updates afterwards
+            long long p0; int pv, pr;
+            geom(ci - 1, p0, pv, pr);
+            for (int l = 0; l < 2; l++) {
+                use(l, b ^ 1);
+                RUN(wait(Gs, e_rank[l]));                          // gv A planes and the scale vectors of latent l are free (rank update of chunk ci - 2)
+                RUN(chunk_kgrad(c, l, theta, p0, pv, pr, Gs));     // needs the likelihood of chunk ci - 1 (G order) and Y (ci - 1, l) (waited for before it)
+                RUN(record(Gs, &e_kgrad[l]));
+            }
+            for (int l = 0; l < 2; l++) {
+                use(l, b ^ 1);
+                RUN(wait(Ms, e_kgrad[l]));
+                RUN(chunk_rank(c, l, pr, Ms));
+                RUN(record(Ms, &e_rank[l]));
+            }
+        }
+        if (ci + 1 < nchunks) {
+            // ---- G: Kmn tiles of chunk ci + 1 into the other copy (K fp64: last read by kgrad (ci - 1), G order; K planes: free once A (ci, l) is done)
+            long long q0; int qv, qr;
+            geom(ci + 1, q0, qv, qr);
+            for (int l = 0; l < 2; l++) {
+                use(l, b ^ 1);
+                RUN(wait(Gs, e_A[l]));
+                RUN(chunk_kgen(c, l, theta, c->X, q0, qv, qr, Gs));
+                RUN(record(Gs, &e_kgen[l]));
+            }
+        }
+        if (ci < nchunks) {
+            // ---- G: likelihood of chunk ci as soon as both latents' statistics exist (it runs beside Y (ci, g)); then kgrad (ci, .) may follow
+            geom(ci, n0, nvalid, rows);
+            use(0, b); use(1, b);
+            RUN(wait(Gs, e_stats));
+            RUN(run_point_kernel(c, theta, c->Y, n0, nvalid, rows, Gs));
+            RUN(record(Gs, &e_point));
+            RUN(wait(Gs, e_Y[0])); RUN(wait(Gs, e_Y[1]));          // kgrad (ci, .) reads Y: order it here so the next iteration need not remember
+        }
+    }
+    use(0, 0); use(1, 0);
+    cudaEvent_t eg = nullptr, em = nullptr;
+    RUN(record(Gs, &eg)); RUN(wait(Ms, eg));
+    if (Ms != st) { RUN(record(Ms, &em)); RUN(wait(st, em)); }
+    return 0;
+}
+
 int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     if (!c->has_data) { c->err = "zigp: no data set (call zigp_set_data_* first)"; return ZIGP_ESTATE; }
     DeviceGuard guard(c->device);
@@ -575,7 +687,9 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
     // likelihood kernel, which needs both): the tensor-core contractions of one latent overlap the fp64 / memory-bound kernels
     // (kgen, kgrad) of the other, and the two O(M^3) M-stages -- chains of small launches that cannot fill the GPU -- run side by side.
     // Results do not depend on the interleaving (no floating-point atomics).
-    const bool two = c->engine == 1 && c->aux != nullptr && !c->profiling;     // per-kernel event timing wants the kernels alone on the GPU
+    // per-kernel event timing wants the kernels alone on the GPU (ZIGP_PROF_TWO=1 keeps both streams: the class times then show how far a
+    // kernel is stretched by what runs beside it)
+    const bool two = c->engine == 1 && c->aux != nullptr && (!c->profiling || getenv("ZIGP_PROF_TWO") != nullptr);
     cudaStream_t sl[2] = {st, two ? c->aux : st};
     auto fork = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0)); } return 0; };
     auto join = [&]() -> int { if (two) { CK(cudaEventRecord(c->ev_join, c->aux)); CK(cudaStreamWaitEvent(st, c->ev_join, 0)); } return 0; };
@@ -587,9 +701,11 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
         RUN(mstage_forward(c, l, theta, sl[l]));
     }
     RUN(join());
-    if (two && c->oz_pipe && c->oz_sched == 1) {
+    if (two && c->oz_pipe && c->oz_sched == 2 && c->lat[0].Kb2[1] != nullptr) {
+        RUN(accumulate_pipelined(c, theta, st));
+    } else if (two && c->oz_pipe && c->oz_sched == 1) {
         // mma / glue schedule.  M = st (contractions), G = aux (everything else).  edge(a, b): work recorded so far on a precedes later work on b.
-        cudaStream_t Ms = st, Gs = c->aux;
+        cudaStream_t Ms = c->hi ? c->hi : st, Gs = c->aux;
         c->evnext = 0;
         auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {
             if (c->evnext == c->evpool.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->evpool.push_back(e); }
@@ -597,7 +713,8 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             CK(cudaEventRecord(e, from)); CK(cudaStreamWaitEvent(to, e, 0));
             return 0;
         };
-        RUN(edge(Ms, Gs));                                  // the M-stage (both latents, joined into st above) precedes everything
+        if (Ms != st) RUN(edge(st, Ms));                    // the M-stage (both latents, joined into st above) precedes everything
+        RUN(edge(st, Gs));
         for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
             const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
             const int rows = (int)rup(nvalid, 512);
@@ -619,6 +736,7 @@ int accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             }
         }
         RUN(edge(Gs, Ms));
+        if (Ms != st) RUN(edge(Ms, st));
     } else
     for (long long n0 = 0; n0 < c->n_local; n0 += c->chunk) {
         const int nvalid = (int)std::min<long long>(c->chunk, c->n_local - n0);
@@ -762,8 +880,13 @@ int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
     const int D = c->D;
     FinalArgs f{};
     f.theta = theta; f.out = out; f.accum = c->accum; f.info = c->info; f.scale = c->scale; f.D = D; f.q_full = c->q_full ? 1 : 0;
+    // the two latents' O(M^3) backward chains are independent and too small to fill the GPU: run them side by side (as the forward M-stage)
+    const bool two = c->aux != nullptr && !c->profiling;
+    cudaStream_t caller = st;
+    if (two) { CK(cudaEventRecord(c->ev_fork, caller)); CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0)); }
     for (int l = 0; l < 2; l++) {
         Latent& L = c->lat[l];
+        cudaStream_t st = (two && l == 1) ? c->aux : caller;      // shadows the parameter inside the loop body
         const int Mp = L.Mp;
         dim3 g2((Mp + 127) / 128, Mp);
         const double* a = L.accV + Mp;     // second row of the vector block
@@ -795,6 +918,7 @@ int finish(zigp_ctx* c, const double* theta, double* out, cudaStream_t st) {
         q.M = L.M; q.Mp = Mp; q.off_ell = L.off_ell; q.off_var = L.off_var; q.off_Z = L.off_Z; q.off_mu = L.off_mu; q.off_s = L.off_s;
         q.accV = L.accV; q.gZmm = L.gZmm; q.pell = L.pell; q.pvar = L.pvar; q.gmu = L.gmu; q.dE = L.dE; q.dK = L.dK; q.s = L.s; q.kl = L.kl;
     }
+    if (two) { CK(cudaEventRecord(c->ev_join, c->aux)); CK(cudaStreamWaitEvent(caller, c->ev_join, 0)); }
     finalize_kernel<<<1, 256, 0, st>>>(f);
     LAUNCHED();
     return 0;
@@ -994,6 +1118,7 @@ int zigp_destroy(zigp_ctx* c) {
     cudaFree(c->pred_x); cudaFree(c->pred_o);
     cudaFree(c->dbg_pa); cudaFree(c->dbg_pb); cudaFree(c->dbg_sa); cudaFree(c->dbg_sb);
     if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->hi) cudaStreamDestroy(c->hi);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->cap) cudaStreamDestroy(c->cap);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1405,8 +1530,14 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
             RUN(balloc((void**)&L.oz_colA, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colAw, (size_t)oz::NS64 * chunk * L.Mp));
             RUN(balloc((void**)&L.oz_colmax, (size_t)2 * L.Mp * sizeof(unsigned long long)));
-            RUN(balloc((void**)&L.oz_gvmax, 2 * sizeof(unsigned long long)));
-            CK(cudaMemset(L.oz_gvmax, 0, 2 * sizeof(unsigned long long)));
+            RUN(balloc((void**)&L.oz_gvmax, 4 * sizeof(unsigned long long)));
+            CK(cudaMemset(L.oz_gvmax, 0, 4 * sizeof(unsigned long long)));
+            // second copies of the forward -> backward hand-over buffers (chunk-pipelined schedule)
+            L.Kb2[0] = L.Kb; L.RAb2[0] = L.RAb; L.gm2[0] = L.gm; L.gv2[0] = L.gv; L.inA2[0] = L.oz_inA; L.gvmax2[0] = L.oz_gvmax; L.gvmax2[1] = L.oz_gvmax + 2;
+            if (c->oz_sched == 2) {
+                DA(L.Kb2[1], chunk * L.Mp); DA(L.RAb2[1], chunk * L.Mp); DA(L.gm2[1], chunk); DA(L.gv2[1], chunk);
+                RUN(balloc((void**)&L.inA2[1], (size_t)oz::NS64 * chunk * L.Mp));
+            }
             DA(L.oz_rs, chunk); DA(L.oz_rsA, chunk); DA(L.oz_csA, L.Mp); DA(L.oz_csAw, L.Mp);
             for (int i = 0; i < 3; i++) {
                 RUN(balloc((void**)&L.ozW[i], (size_t)oz::NS64 * L.Mp * L.Mp));
@@ -1416,6 +1547,11 @@ int zigp_set_engine(zigp_ctx* c, int engine) {
         }
         if (!getenv("ZIGP_ONE_STREAM")) {
             CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+            if (!getenv("ZIGP_NO_PRIO")) {
+                int lo = 0, hi = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // numerically lower = higher priority
+                CK(cudaStreamCreateWithPriority(&c->hi, cudaStreamNonBlocking, hi));
+            }
             CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         }
