@@ -183,6 +183,7 @@ def parity_block(ctx, theta, out, stream, sample, order, cond=None, shard=None, 
            "grad_worst_block": worst_name, "points": int(Xc.shape[0]), "against": "oracle (CPU float64 restatement, pinned to the reference's source by tests/golden)",
            "info": int(o[3])}
     if shard is not None:
+        blk["points"] = int(np.asarray(X).shape[0])
         blk["ranks"] = shard[1]; blk["path"] = "accumulate on every rank's slice of the sample -> NCCL all-reduce of the packed accumulator -> finish"
     if cond is not None:
         blk["cond_kmm"] = cond

@@ -183,5 +183,6 @@ if __name__ == "__main__":
     synth_case("cfg3_M1024", 16384, 1024, 1024, 3, 32, 1 << 24)   # BASELINE configs[3] at its own M = 1024, D = 3: a 16384-point batch of N = 2^24
     synth_case("illcond", 6000, 144, 144, 2, 33, ell_factor=1.5, grad_tol=1e-6)   # lengthscale 1.5 h: cond(Kmm) ~ 6e6 (profiles/cond_study_r01.txt)
     kron_synth_case("small", 1500, 12, 20, 21, 4500)          # shrunken configs[4]; minibatch scale 3
+    kron_synth_case("cfg4_64x64", 768, 64, 64, 22, 1 << 26)   # BASELINE configs[4] at its own grid (64 x 64, M = 4096): a 768-point batch of N = 2^26
     kron_pptr_case()                                          # configs[1] on the reference's own data
     print("golden fixtures written to", HERE)

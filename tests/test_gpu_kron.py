@@ -77,8 +77,12 @@ def golden_case(name):
     return d, X, Y, p
 
 
-def test_golden_kron_synthetic():
-    d, X, Y, p = golden_case("kron_small")
+@pytest.mark.parametrize("name", ["kron_small", "kron_cfg4_64x64"])
+def test_golden_kron_synthetic(name):
+    """kron_small: shrunken configs[4]; kron_cfg4_64x64: BASELINE configs[4] at its own 64 x 64 grid (M = 4096), a 768-point batch of N = 2^26.
+    Values: the reference's scripts/onoff.py functions through oracle/refshim"""
+    d, X, Y, p = golden_case(name)
+    assert str(d["source"]) == "reference-via-shim"
     m, out, gc, gf = evaluate(X, Y, p, num_data=int(d["num_data"]))
     check(out, gc, gf, d, 1e-9, 1e-12)
     pred = np.concatenate(m.predict_onoff(X[:64])["all"], 1)

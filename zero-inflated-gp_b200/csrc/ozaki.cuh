@@ -470,6 +470,7 @@ struct OzArgs {
     int8_t* sl_rows; double* sl_rscale;         // planes[p][r][c] (row operand of the next product), scale per row    (may be null)
     int8_t* sl_cols; double* sl_cscale;         // planes[p][c][r] (transposed: operand of the rank update), scale per column (may be null)
     long long sl_stride;                        // plane stride in bytes (rows * cols)
+    int trace;                                  // ZIGP_OZ_EXP == 9 builds: record the phase timestamps of CTA 0 for this launch
 };
 
 __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
@@ -481,7 +482,7 @@ __host__ __device__ inline int lower_tile_count(int ntr, int ntcg, int CL) {
 #if ZIGP_OZ_EXP == 9
 // experiment: phase timestamps (SM clock) of CTA 0: per computed tile [mma_start, mma_issued, epi_wait, epi_full, drain_end, write_end, 0, 0]
 __device__ long long oz_trace[8 * 256];
-#define OZ_TRACE(slot, idx) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 256) oz_trace[(slot) * 8 + (idx)] = clock64(); } while (0)
+#define OZ_TRACE(slot, idx) do { if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 256) oz_trace[(slot) * 8 + (idx)] = clock64(); } while (0)
 #else
 #define OZ_TRACE(slot, idx) do { } while (0)
 #endif

@@ -408,6 +408,9 @@ int oz_product(zigp_ctx* c, Latent& L, int wi, bool from_A, int rows, int tri, d
         a.sl_bound2 = bound2; a.sl_rows = L.oz_inA; a.sl_rscale = L.oz_rsA; a.sl_stride = (long long)rows * Mp;
         if (reslice > 1) { a.sl_cols = L.oz_colA; a.sl_cscale = L.oz_csA; }
     }
+#if ZIGP_OZ_EXP == 9
+    { const char* tw = getenv("ZIGP_OZ_TRACE_WI"); a.trace = (tw && atoi(tw) == wi) ? 1 : 0; }
+#endif
     ProfScope ps(c, PC_GEMM, st);
     CK(oz::launch_ozaki_gemm((wi == 2 && c->oz_ns_grad && c->oz_ns == oz::NS64) ? c->oz_ns_grad : c->oz_ns, A, B, a, st));   // wi == 2: Y = G A feeds gradients only
     c->launches++;
@@ -1363,6 +1366,7 @@ int zigp_debug_gemm(zigp_ctx* c, int engine, const double* In, int64_t ldi, cons
     oz::OzOperand A{c->dbg_pa, kdim, rows, (long long)rows * kdim, c->dbg_sa}, B{c->dbg_pb, kdim, cols, (long long)cols * kdim, c->dbg_sb};
     oz::OzArgs g{};
     g.Out = Out; g.ldo = ldo; g.alpha = 1.0; g.beta = 0.0; g.rows = rows; g.cols = cols; g.kdim = kdim; g.tri = tri; g.stat_sq = stat_sq; g.nsplit = 1;
+    g.trace = 1;
     CK(oz::launch_ozaki_gemm(c->oz_ns, A, B, g, st));
     c->launches++;
     return ZIGP_OK;
