@@ -127,8 +127,9 @@ int zigp_predict_host(zigp_ctx* ctx, const double* theta_host, const double* Xne
  * return it, so bindings read it here (zigp_predict_host does, and returns ZIGP_ENOTPD). */
 int zigp_read_info(zigp_ctx* ctx, int64_t* info, void* stream);
 
-/* Test / profiling hooks: view of an internal device buffer after the last call.
- * name: "L","T","Kmm","alpha_w","beta","E","a","G","K","A","RA","V","Y","mean","var","gm","gv" ; latent 0 = f, 1 = g. */
+/* Test / profiling hooks: view of an internal device buffer after the last call (dense contexts).
+ * name: "L","T","Tt","R","Rt","alpha_w","beta","dK","kl","E","accE","accV","G","Hs","P","K","A","Y","V","mean","var","gm","gv" ; latent 0 = f, 1 = g.
+ * "A" and "V" are written by the DMMA engine and by the r1 int8 pipeline only: the planes pipeline keeps A as digit planes. */
 int zigp_debug_buffer(zigp_ctx* ctx, const char* name, int latent, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
 /* Contraction engine of the dense path: 0 = DMMA (fp64 mma.sync), 1 = fp64 emulated exactly-sliced on the INT8 tensor
  * cores (tcgen05.mma kind::i8; csrc/ozaki.cuh: 7 x 8-bit slices per operand, int32 accumulation in TMEM, fp64 recombination --

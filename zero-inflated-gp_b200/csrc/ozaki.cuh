@@ -90,6 +90,23 @@ __device__ __forceinline__ void slice_bytes(double t, uint32_t& lo, uint32_t& hi
     }
 }
 
+// the same from the PRE-SCALED value: NS = 7: v1 = t 2^28, NS = 4: t 2^32 (callers that fold the power-of-two factors into one multiplier);
+// bit-identical digits (the products by 2^28 / 2^32 are exact; the fused multiply-add rounds once, like the separate exact product + addition)
+template <int NS>
+__device__ __forceinline__ void slice_bytes_pre(double v1, uint32_t& lo, uint32_t& hi) {
+    if (NS == 7) {
+        const double s1 = v1 + RMAGIC;
+        const int h1 = __double2loint(s1);
+        const int h2 = __double2loint(fma(v1 - (s1 - RMAGIC), 268435456.0, RMAGIC));
+        const unsigned long long U = (unsigned long long)(((long long)h1 << 28) + (long long)h2) + 0x0080808080808080ULL;
+        const unsigned long long X = U ^ 0x0080808080808080ULL;
+        lo = (uint32_t)X; hi = (uint32_t)(X >> 32);
+    } else {
+        const uint32_t w = (uint32_t)__double2loint(v1 + RMAGIC);
+        lo = (w + 0x80808080u) ^ 0x80808080u; hi = 0;
+    }
+}
+
 // digit p of the sliced value as the byte selector of __byte_perm: (word, byte) = (hi, 2 - p) for p < 3, (lo, 6 - p) otherwise (NS = 7)
 template <int NS>
 __device__ __forceinline__ uint32_t plane_word4(int p, const uint32_t (&lo)[4], const uint32_t (&hi)[4]) {
@@ -654,6 +671,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
         const int q = warp & 3, h = (warp - 2) >> 2;
         const int rl = q * 32 + lane;
         uint32_t ti = 0;
+        // fused re-slicing: one power-of-two scale for the whole launch, computed once (a global load issued after the accumulators arrive waits
+        // ~2000 cycles behind the MMAs' operand traffic, and sqrt / ilogb / scalbn are long sequences: none of it belongs on the per-tile path)
+        const bool reslice = g.sl_bound2 != nullptr;
+        double sl_inv = 0.0, sl_sc = 0.0;
+        if (reslice) {
+            const int e = ilogb(sqrt(g.sl_bound2[0])) + EOFF;
+            sl_inv = scalbn(1.0, -e);
+            sl_sc = scalbn(1.0, e);
+        }
         for (int ct = (int)cid; ct < ntiles; ct += (int)ncl) {
             int row0, col0, kb, ke, ckb, cke; bool compute, any;
             tile_geom(ct, row0, col0, kb, ke, ckb, cke, compute, any);
@@ -662,9 +688,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             const int tc = col0 / OBN;
             // this lane's column scale, dot-vector entry and row scale, requested while the MMAs of the tile are still running; the epilogue
             // broadcasts them by shuffle (a global load issued after the accumulators arrive waits ~2000 cycles behind the MMA's operand traffic)
-            const double cs_l = __ldg(g.cscale + col0 + h * CW + (lane & (CW - 1)));
+            // this lane's column scale (exact power of two: only its biased exponent is kept), dot-vector entry and the row scale, requested
+            // while the MMAs of the tile are still running (a global load issued after the accumulators arrive waits ~2000 cycles behind the
+            // MMAs' operand traffic); the epilogue broadcasts them by shuffle
+            const int ce_l = (__double2hiint(__ldg(g.cscale + col0 + h * CW + (lane & (CW - 1)))) >> 20) & 0x7ff;
             const double dv_l = g.dotvec ? __ldg(g.dotvec + col0 + h * CW + (lane & (CW - 1))) : 0.0;
-            const double rs = g.rscale[r] * INVB2;
+            // row scale x 2^-16 as an exponent offset: element scale = 2^(ce - 1023 + er), built in the integer pipe -- ONE fp64 multiply per
+            // element.  fp64 instructions of the epilogue issue at ~1/8 of their nominal rate while the tensor pipe is busy (math-pipe throttle:
+            // profiles/int8_epilogue_r02.txt), so the post-drain phase is as long as its fp64 instruction count
+            const int er = ((__double2hiint(g.rscale[r]) >> 20) & 0x7ff) - 1023 - 2 * SBITS;
             if (warp == 2 && lane == 0) OZ_TRACE(ti, 2);
             tc05::mbar_wait(tmem_full, ti & 1u);
             tc05::fence_after_thread_sync();
@@ -707,20 +739,55 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
             double* Out = g.Out + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0);
             const double* Zin = g.Zin ? g.Zin + (g.nsplit > 1 ? (long long)blockIdx.y * g.split_stride : 0) : nullptr;
             double ssq = 0.0, sdt = 0.0;
-            const bool reslice = g.sl_bound2 != nullptr;
-            double sl_inv = 0.0;
             if (reslice) {
-                const int e = ilogb(sqrt(g.sl_bound2[0])) + EOFF;
-                sl_inv = scalbn(1.0, -e);
-                const double sc = scalbn(1.0, e);
-                if (g.sl_rscale && col0 == 0 && h == 0) g.sl_rscale[r] = sc;
-                if (g.sl_cscale && row0 == 0 && q == 0 && lane < CW) g.sl_cscale[col0 + h * CW + lane] = sc;
+                if (g.sl_rscale && col0 == 0 && h == 0) g.sl_rscale[r] = sl_sc;
+                if (g.sl_cscale && row0 == 0 && q == 0 && lane < CW) g.sl_cscale[col0 + h * CW + lane] = sl_sc;
             }
             uint32_t wr[NCH][NS][4];
+            // Lean path of the planes pipeline's A product (digit planes + statistics, no fp64 output): the slicing scale and the 2^28 (2^32) of
+            // the digit extraction are folded into the element's power-of-two multiplier, the statistics are taken on the pre-scaled value and
+            // rescaled once per tile (exact: powers of two) -- 7 fp64 instructions per element instead of 12, bit-identical results.
+            const bool lean = reslice && g.sl_rows != nullptr && g.Out == nullptr && g.OutSq == nullptr && g.sl_cols == nullptr && g.beta == 0.0 &&
+                              g.alpha == 1.0;
+            if (lean) {
+                constexpr int SH = (NS == 7) ? 28 : 32;
+                const int es = 1023 - ((__double2hiint(sl_inv) >> 20) & 0x7ff);       // sl_inv = 2^-es
+                const int eoff = er - es + SH;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        uint32_t lo[4], hi[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int ec = __shfl_sync(0xffffffffu, ce_l, ch * 16 + j + i);
+                            const double t = acc[ch][j + i] * __hiloint2double((ec + eoff) << 20, 0);
+                            ssq = fma(t, t, ssq);
+                            if (g.dotvec) sdt = fma(t, __shfl_sync(0xffffffffu, dv_l, ch * 16 + j + i), sdt);
+                            slice_bytes_pre<NS>(t, lo[i], hi[i]);
+                        }
+#pragma unroll
+                        for (int p = 0; p < NS; p++) wr[ch][p][j >> 2] = plane_word4<NS>(p, lo, hi);
+                    }
+                }
+                const double back = __hiloint2double((1023 + es - SH) << 20, 0);           // v = t 2^(es - SH)
+                ssq *= back * back; sdt *= back;
+            } else {
+            // scale: power-of-two row and column scales as ONE multiplier built from their exponents; alpha only when it is not 1
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) acc[ch][j] = g.alpha * (acc[ch][j] * rs * __shfl_sync(0xffffffffu, cs_l, ch * 16 + j));
+                for (int j = 0; j < 16; j++) {
+                    const int ec = __shfl_sync(0xffffffffu, ce_l, ch * 16 + j);
+                    acc[ch][j] = acc[ch][j] * __hiloint2double((ec + er) << 20, 0);
+                }
+            }
+            if (g.alpha != 1.0) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc[ch][j] *= g.alpha;
+                }
             }
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++) {
@@ -765,6 +832,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const __grid_
                         }
                     }
                 }
+            }
             }
             if (reslice && g.sl_rows) {
                 int8_t* orow = g.sl_rows + (long long)r * g.cols + col0 + h * CW;
