@@ -433,8 +433,9 @@ def run_ours(a):
     ctx.set_profiling(False)
     alg, exe = ctx.flop_counts()
     gemm_ms, gemm_n = prof["gemm_tn"]
-    # dominant kernel: gemm_tn_f64<64,64,32,32,2,3>; one launch = one triangular product of a chunk of points with an
-    # M x M triangular factor: M^2 flop per point (each of the six products per latent is M^2 flop)
+    # DMMA engine: dominant kernel gemm_tn_f64<64,64,32,32,2,3>; one launch = one triangular product of a chunk of points with an
+    # M x M triangular factor: M^2 flop per point (each of the six products per latent is M^2 flop).  The default int8 engine's
+    # dominant kernel (ozaki_gemm_kernel, all four contraction launches of a chunk-latent) is accounted for below.
     flops_per_launch = float(M) * M * (n_loc / max(1, gemm_n / 8))      # 8 launches per chunk (4 per latent)
     achieved = flops_per_launch / (gemm_ms / max(1, gemm_n) * 1e-3) * 1e-12 if gemm_n else 0.0
     int8 = (not kron) and getattr(m, "engine", "dmma") == "int8"
