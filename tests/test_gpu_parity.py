@@ -205,6 +205,19 @@ def test_not_positive_definite_is_reported():
     m = synth.build_model(X, Y, p, jitter=0.0)
     with pytest.raises(_cabi.NotPositiveDefiniteError):
         m.compute_log_likelihood()
+    # the predict and KL paths surface it too (the reference: InvalidArgumentError from tf.cholesky), device- and host-pointer entries alike
+    with pytest.raises(_cabi.NotPositiveDefiniteError):
+        m.predict_onoffgp(X[:10])
+    with pytest.raises(_cabi.NotPositiveDefiniteError):
+        m.compute_prior_KL()
+    out9 = np.empty((9, 10))
+    theta = synth.pack_theta(p)
+    with pytest.raises(_cabi.NotPositiveDefiniteError):
+        m._ctx.call("zigp_predict_host", theta.ctypes.data, np.ascontiguousarray(X[:10]).ctypes.data, 10, out9.ctypes.data, None)
+    # and a healthy model on the same context type predicts normally afterwards
+    p2 = synth.make_params(M, M, D, 8)
+    m2 = synth.build_model(X, Y, p2)
+    assert all(np.all(np.isfinite(o)) for o in m2.predict_onoffgp(X[:10]))
 
 
 def test_host_pointer_entry_points_match_device_entry_points():

@@ -111,14 +111,15 @@ struct KronKgradArgs {
     const double* X; int xstride, xoff; long long n0; int nvalid;
     const double* Z; int M, D, Mp;
     double* partial;     // [nslots][1 + 2*D][Mp]
+    int rpb;             // rows per block (kg_rows_per_block)
 };
 
 __global__ void __launch_bounds__(64) kron_kgrad_kernel(const KronKgradArgs p) {
     __shared__ double sx[KG_ROWS][ZIGP_MAX_D];
     __shared__ double sdp[KG_ROWS];
     const int m = blockIdx.x * 64 + threadIdx.x;
-    const int r0 = blockIdx.y * KG_ROWS;
-    const int nr = min(KG_ROWS, p.nvalid - r0);
+    const int r0 = blockIdx.y * p.rpb;
+    const int nr = min(p.rpb, p.nvalid - r0);
     if (nr <= 0) return;
     for (int e = threadIdx.x; e < nr * p.D; e += 64) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0 + e / p.D) * p.xstride + p.xoff + e % p.D];
     for (int e = threadIdx.x; e < nr; e += 64) sdp[e] = -p.gv[r0 + e] * p.po[r0 + e];

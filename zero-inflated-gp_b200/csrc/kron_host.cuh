@@ -129,7 +129,8 @@ int kron_chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, i
         k.KV = F.KVb; k.U = F.Ub; k.K = F.Kb; k.ld = F.Mp; k.gv = L.gv; k.po = O.p;
         k.X = c->X; k.xstride = c->Ds + c->Dt; k.xoff = F.xoff; k.n0 = n0; k.nvalid = nvalid;
         k.Z = theta + F.off_Z; k.M = F.M; k.D = F.D; k.Mp = F.Mp; k.partial = F.kg_partial;
-        dim3 gg(F.Mp / 64, (rows + KG_ROWS - 1) / KG_ROWS);
+        k.rpb = kg_rows_per_block(rows, KG_ROWS);
+        dim3 gg(F.Mp / 64, (rows + k.rpb - 1) / k.rpb);
         ProfScope ps(c, PC_KGRAD, st);
         kron_kgrad_kernel<<<gg, 64, 0, st>>>(k);
         LAUNCHED();
@@ -331,7 +332,7 @@ int kron_alloc(zigp_ctx* c, const int Ms[2], const int Mt[2]) {
 
     const long long chunk = c->chunk;
     c->pt_slots = (int)(chunk / 256);
-    c->kg_slots = (int)((chunk + KG_ROWS - 1) / KG_ROWS);
+    c->kg_slots = kg_slot_count(c->chunk, KG_ROWS);
     long long acc_len = 4;
     for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];

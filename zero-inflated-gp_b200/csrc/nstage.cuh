@@ -1,6 +1,7 @@
 // N-stage kernels that are not contractions: Kmn tile construction, the per-point closed-form on/off likelihood
 // (forward and backward), the Kmn-side kernel-gradient reductions, and the predict epilogue.
 #pragma once
+#include <algorithm>
 #include "mstage.cuh"
 
 namespace zigp {
@@ -202,6 +203,16 @@ __global__ void __launch_bounds__(256) point_kernel(const PointArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int KG_ROWS = 256;        // Kronecker variant (kron.cuh)
 constexpr int KGD_ROWS = 128;       // dense path: 8 x chunk/128 blocks (4.6 waves at 65536 rows instead of 2.3: the tail wave cost 20 %), 10 KB of shared memory
+// Rows per block at run time.  Every thread of these kernels walks its block's rows serially (~0.9 us per row of dependent loads): at the
+// full block height a toy-sized evaluation spent 110 us per launch in a single wave of a few CTAs (profiles/launches_r02_toy.csv: 20 % of the
+// whole evaluation).  Small chunks therefore use 16-row blocks (more CTAs, 8 x shorter chains); large chunks keep the tuned heights.
+constexpr int KG_SMALL_ROWS = 16;
+constexpr int KG_SMALL_LIMIT = 16384;        // chunks of at most this many (padded) rows use KG_SMALL_ROWS
+__host__ __device__ inline int kg_rows_per_block(int rows, int full) { return rows <= KG_SMALL_LIMIT ? KG_SMALL_ROWS : full; }
+inline int kg_slot_count(long long chunk, int full) {       // slots a context needs for chunks of up to `chunk` rows
+    const long long big = (chunk + full - 1) / full, small = (std::min<long long>(chunk, KG_SMALL_LIMIT) + KG_SMALL_ROWS - 1) / KG_SMALL_ROWS;
+    return (int)std::max(big, small);
+}
 struct KgradArgs {
     const double* K; const double* Y; const double* A; long long ld;
     const double* gm; const double* gv; const double* beta;
@@ -210,6 +221,7 @@ struct KgradArgs {
     double* partial;     // [nslots][2 + 2*D][Mp]
     double* Aw;          // out: gv[n] * A[n,m]  (row-scaled copy consumed by syrk_nt_f64), same ld; null with the int8 engine
     unsigned long long* cmaxA; unsigned long long* cmaxAw;   // int8 engine: per-column max |A|, max |gv A| over the chunk (bit patterns)
+    int rpb;             // rows per block (kg_rows_per_block)
 };
 
 #ifndef ZIGP_KG_UNROLL
@@ -224,10 +236,10 @@ __global__ void __launch_bounds__(128, (DT <= 4 ? ZIGP_KG_MINB : 1)) kgrad_kerne
     __shared__ double sx[KGD_ROWS][DT];
     __shared__ double sgm[KGD_ROWS], sgv[KGD_ROWS];
     const int m = blockIdx.x * 128 + threadIdx.x;
-    const int r0 = blockIdx.y * KGD_ROWS;
-    const int nr = min(KGD_ROWS, p.nvalid - r0);
+    const int r0 = blockIdx.y * p.rpb;
+    const int nr = min(p.rpb, p.nvalid - r0);
     if (nr <= 0) {                                     // padding rows of the chunk: Aw must still be defined (zero)
-        const int nz = min(KGD_ROWS, p.rows - r0);
+        const int nz = min(p.rpb, p.rows - r0);
         if (p.Aw) for (int r = 0; r < nz; r++) p.Aw[(long long)(r0 + r) * p.ld + m] = 0.0;
         return;
     }
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(128, (DT <= 4 ? ZIGP_KG_MINB : 1)) kgrad_kerne
             if (d < p.D) { double df = sx[r][d] - z[d]; s1[d] = fma(G, df, s1[d]); q[d] = fma(G * df, df, q[d]); }
         }
     }
-    if (p.Aw) for (int r = nr; r < min(KGD_ROWS, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
+    if (p.Aw) for (int r = nr; r < min(p.rpb, p.rows - r0); r++) Awp[(long long)r * p.ld] = 0.0;   // ragged tail of the chunk
     if (p.cmaxA) {
         atomicMax(p.cmaxA + m, (unsigned long long)__double_as_longlong(mxa));
         atomicMax(p.cmaxAw + m, (unsigned long long)__double_as_longlong(mxw));

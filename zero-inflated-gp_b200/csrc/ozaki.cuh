@@ -368,6 +368,7 @@ struct KgradPArgs {
     const unsigned long long* gvmax;                           // bit pattern of max_n |gv_n| over the chunk
     double* partial;                                           // [nslots][2 + 2 D][Mp]
     double* a_scale; double* aw_scale;                         // out [Mp]: the two scales, as per-row scale vectors of the rank update's operands
+    int rpb;                                                   // rows per block (kg_rows_per_block: 16 for small chunks, KGP_ROWS otherwise)
 };
 
 template <int NS, int DT>
@@ -375,9 +376,9 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     __shared__ double sx[KGP_ROWS][DT];
     __shared__ double sgm[KGP_ROWS], sgv[KGP_ROWS];
     const int m0 = blockIdx.x * (KGP_THREADS * 4) + threadIdx.x * 4;
-    const int r0 = blockIdx.y * KGP_ROWS;
-    const int nr = max(0, min(KGP_ROWS, p.nvalid - r0));
-    const int nrow = min(KGP_ROWS, p.rows - r0);                       // rows of this block inside the padded chunk
+    const int r0 = blockIdx.y * p.rpb;
+    const int nr = max(0, min(p.rpb, p.nvalid - r0));
+    const int nrow = min(p.rpb, p.rows - r0);                          // rows of this block inside the padded chunk
     for (int e = threadIdx.x; e < nr * p.D; e += KGP_THREADS) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
     for (int e = threadIdx.x; e < nr; e += KGP_THREADS) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
     __syncthreads();
@@ -453,8 +454,9 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     }
 }
 
-inline cudaError_t launch_kgrad_planes(int ns, const KgradPArgs& k, cudaStream_t st) {
-    const dim3 grid((k.Mp + KGP_THREADS * 4 - 1) / (KGP_THREADS * 4), (k.rows + KGP_ROWS - 1) / KGP_ROWS);
+inline cudaError_t launch_kgrad_planes(int ns, KgradPArgs k, cudaStream_t st) {
+    k.rpb = kg_rows_per_block(k.rows, KGP_ROWS);
+    const dim3 grid((k.Mp + KGP_THREADS * 4 - 1) / (KGP_THREADS * 4), (k.rows + k.rpb - 1) / k.rpb);
 #define ZIGP_KGP(NSV, DTV) kgrad_planes_kernel<NSV, DTV><<<grid, KGP_THREADS, 0, st>>>(k)
 #define ZIGP_KGP_D(NSV)                                  \
     switch (k.D) {                                       \

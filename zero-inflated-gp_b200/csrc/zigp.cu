@@ -548,7 +548,8 @@ int chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, int nv
         k.Aw = nullptr; k.cmaxA = L.oz_colmax; k.cmaxAw = L.oz_colmax + L.Mp;
         CK(cudaMemsetAsync(L.oz_colmax, 0, (size_t)2 * L.Mp * sizeof(unsigned long long), st));
     }
-    dim3 gg(L.Mp / 128, (rows + KGD_ROWS - 1) / KGD_ROWS);
+    k.rpb = kg_rows_per_block(rows, KGD_ROWS);
+    dim3 gg(L.Mp / 128, (rows + k.rpb - 1) / k.rpb);
     {
         ProfScope ps(c, PC_KGRAD, st);
         launch_kgrad(k, gg, st);
@@ -989,7 +990,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     chunk = rup(chunk, 512);
     c->chunk = chunk;
     c->pt_slots = (int)(chunk / 256);
-    c->kg_slots = (int)((chunk + KGD_ROWS - 1) / KGD_ROWS);
+    c->kg_slots = kg_slot_count(chunk, KGD_ROWS);
     // packed accumulator: header(4) + per latent [E (Mp^2), vec block (2+2D) Mp]
     long long acc_len = 4;
     for (int l = 0; l < 2; l++) {

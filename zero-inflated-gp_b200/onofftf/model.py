@@ -17,7 +17,7 @@ from onoffgpf.model import wrap_device_buffer
 from onoffgpf.param import DTYPE, Log1pe, Param, Parameterized, positive
 
 JITTER_LEVEL = 1e-5           # scripts/onoff.py:18
-DEFAULT_CHUNK_ROWS = 524288   # ~40 launches per chunk and latent: large chunks amortise them (61.6 vs 27.3 Mpts/s at 64 x 64, N = 2^22)
+DEFAULT_CHUNK_ROWS = 2097152  # ~40 launches per chunk and latent: large chunks amortise them (63.5 / 66.5 / 67.3 M points/s at 524288 / 1048576 / 2097152 rows, 64 x 64, N = 2^25; 20 KB of workspace per row)
 
 
 class DataSet:
