@@ -38,7 +38,7 @@ int kron_mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st
         dim3 g2((F.Mp + 127) / 128, F.Mp);
         kmm_build_kernel<<<g2, 128, 0, st>>>(theta + F.off_Z, theta + F.off_ell, theta + F.off_var, F.M, F.D, F.Mp, c->jitter, F.Lb);
         LAUNCHED();
-        CholBufs cb{F.Lb, F.Lt, F.T, F.Tt, F.Dinv, F.Dinvt, F.Xtmp, F.Mp, F.nb};
+        CholBufs cb{F.Lb, F.Lt, F.T, F.Tt, F.Dinv, F.Dinvt, F.Xtmp, F.Mp, F.nb, F.M};
         RUN(chol_inverse(c, cb, l * 2 + p, st));
         rowop_kernel<<<(F.Mp + 7) / 8, 256, 0, st>>>(F.Tt, nullptr, nullptr, nullptr, F.d, F.Mp, 1);     // d_i = sum_k T[k,i]^2 = (K^-1)_ii
         LAUNCHED();

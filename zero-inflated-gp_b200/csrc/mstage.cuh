@@ -248,6 +248,12 @@ __global__ void colscale_kernel(const double* __restrict__ In, double* __restric
     if (k < Mp) Out[(long long)i * Mp + k] = In[(long long)i * Mp + k] * colscale[k];
 }
 
+// A[i][i] = 1 for i >= from (the rest of those rows and columns is already zero): the identity tail of T for the padding rows
+__global__ void identity_tail_kernel(double* __restrict__ A, int Mp, int from) {
+    const int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Mp) A[(long long)i * Mp + i] = 1.0;
+}
+
 // copy a NB x NB block (ld NB) into a block of a big matrix
 __global__ void copy_block_kernel(const double* __restrict__ src, double* __restrict__ dst, long long ldd) {
     for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(long long)(e / NB) * ldd + e % NB] = src[e];

@@ -281,7 +281,7 @@ int gemmM(zigp_ctx* c, const double* In, long long ldi, const double* W, long lo
         if (r_) return r_;       \
     } while (0)
 
-struct CholBufs { double *Lb, *Lt, *T, *Tt, *Dinv, *Dinvt, *Xtmp; int Mp, nb; };
+struct CholBufs { double *Lb, *Lt, *T, *Tt, *Dinv, *Dinvt, *Xtmp; int Mp, nb; int M = 0; };
 
 // Lb holds Kmm + jitter I (padding = identity) on entry.  Blocked right-looking Cholesky (diagonal 64-blocks factorised and
 // inverted in shared memory, panels / trailing updates through the DMMA engine), then T = L^-1 by block columns.
@@ -291,15 +291,20 @@ int chol_inverse(zigp_ctx* c, const CholBufs& b, int tag, cudaStream_t st) {
     const int Mp = b.Mp;
     const long long MM = (long long)Mp * Mp;
     dim3 g2((Mp + 127) / 128, Mp);
+    // 64-blocks that hold real rows; the blocks behind them are pure padding (identity rows and columns of Kmm: L = T = I there, every panel
+    // that touches them is zero), so they are neither factorised nor multiplied -- M = 9 pads to Mp = 128, and half of a toy evaluation's
+    // M-stage was spent on the identity block (profiles/launches_r02_toy.csv)
+    const int nreal = b.M > 0 ? std::min(b.nb, (b.M + NB - 1) / NB) : b.nb;
+    const int Mr = nreal * NB;
     // blocked right-looking Cholesky
-    for (int kb = 0; kb < b.nb; kb++) {
+    for (int kb = 0; kb < nreal; kb++) {
         double* diag = b.Lb + (long long)kb * NB * (Mp + 1);
         if (c->potrf_panel)
             potrf_diag_panel_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, b.Dinv + (long long)kb * NB * NB, b.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, tag);
         else
             potrf_diag_kernel<<<1, 256, POTRF_SMEM, st>>>(diag, Mp, b.Dinv + (long long)kb * NB * NB, b.Dinvt + (long long)kb * NB * NB, c->info, kb * NB, tag);
         LAUNCHED();
-        const int rem = Mp - (kb + 1) * NB;
+        const int rem = Mr - (kb + 1) * NB;
         if (rem > 0) {
             double* panel = b.Lb + (long long)(kb + 1) * NB * Mp + (long long)kb * NB;
             RUN(gemmM(c, panel, Mp, b.Dinv + (long long)kb * NB * NB, NB, panel, Mp, nullptr, 0, 1.0, 0.0, rem, NB, NB, st));
@@ -312,12 +317,16 @@ int chol_inverse(zigp_ctx* c, const CholBufs& b, int tag, cudaStream_t st) {
     dim3 gt(Mp / 32, Mp / 32), bt(32, 8);
     transpose_kernel<<<gt, bt, 0, st>>>(b.Lb, b.Lt, Mp, nullptr);
     LAUNCHED();
-    // T = L^-1 by block columns, last to first
+    // T = L^-1 by block columns, last to first; the padding part of T is the identity
     CK(cudaMemsetAsync(b.T, 0, MM * sizeof(double), st));
-    for (int jb = b.nb - 1; jb >= 0; jb--) {
+    if (nreal < b.nb) {
+        identity_tail_kernel<<<(Mp - Mr + 255) / 256, 256, 0, st>>>(b.T, Mp, Mr);
+        LAUNCHED();
+    }
+    for (int jb = nreal - 1; jb >= 0; jb--) {
         copy_block_kernel<<<1, 256, 0, st>>>(b.Dinv + (long long)jb * NB * NB, b.T + (long long)jb * NB * (Mp + 1), Mp);
         LAUNCHED();
-        const int i0 = (jb + 1) * NB, rem = Mp - i0;
+        const int i0 = (jb + 1) * NB, rem = Mr - i0;
         if (rem > 0) {
             RUN(gemmM(c, b.T + (long long)i0 * Mp + i0, Mp, b.Lt + (long long)jb * NB * Mp + i0, Mp, b.Xtmp, NB, nullptr, 0, 1.0, 0.0, rem, NB, rem, st));
             RUN(gemmM(c, b.Xtmp, NB, b.Dinvt + (long long)jb * NB * NB, NB, b.T + (long long)i0 * Mp + (long long)jb * NB, Mp, nullptr, 0, -1.0, 0.0, rem, NB, NB, st));
@@ -343,7 +352,7 @@ int mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st) {
         pad_vec_kernel<<<(Mp + 127) / 128, 128, 0, st>>>(theta + L.off_s, L.s, M, Mp);
         LAUNCHED();
     }
-    CholBufs cb{L.Lb, L.Lt, L.T, L.Tt, L.Dinv, L.Dinvt, L.Xtmp, Mp, L.nb};
+    CholBufs cb{L.Lb, L.Lt, L.T, L.Tt, L.Dinv, L.Dinvt, L.Xtmp, Mp, L.nb, M};
     RUN(chol_inverse(c, cb, l, st));
     const int rb = (Mp + 7) / 8;
     if (c->whiten || c->q_full) {
