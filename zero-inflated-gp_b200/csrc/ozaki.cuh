@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) kgen_sliced_kernel(const double* __restri
                 k[j] = (m0 + j < M) ? v * exp(-0.5 * r2) : 0.0;
             }
         }
-        tc05::st_global_f64x4(K + (long long)r * Mp + m0, k[0], k[1], k[2], k[3]);
+        if (K) tc05::st_global_f64x4(K + (long long)r * Mp + m0, k[0], k[1], k[2], k[3]);     // null: the planes pipeline keeps K as digit planes only
         uint32_t lo[4], hi[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) slice_bytes<NS>(k[j] * inv, lo[j], hi[j]);
@@ -359,7 +359,9 @@ constexpr int KGP_THREADS = 64;
 #endif
 constexpr int KGP_UNROLL = ZIGP_KGP_UNROLL;
 struct KgradPArgs {
-    const double* K; const double* Y; long long ld;
+    const double* K;                                           // fp64 K, or null: K is rebuilt from its digit planes Kp (sliced under 2^e > 4 var)
+    const int8_t* Kp;
+    const double* Y; long long ld;
     const int8_t* Ap; int8_t* Awp; long long pstride;          // planes of A (in) and of gv * A (out), plane stride in bytes
     const double* gm; const double* gv; const double* beta;
     const double* X; long long n0; int nvalid, rows;
@@ -371,7 +373,7 @@ struct KgradPArgs {
     int rpb;                                                   // rows per block (kg_rows_per_block: 16 for small chunks, KGP_ROWS otherwise)
 };
 
-template <int NS, int DT>
+template <int NS, int DT, bool KPL>
 __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kgrad_planes_kernel(const KgradPArgs p) {
     __shared__ double sx[KGP_ROWS][DT];
     __shared__ double sgm[KGP_ROWS], sgv[KGP_ROWS];
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     const double gmx = __longlong_as_double((long long)p.gvmax[0]);
     const int ew = (gmx > 0.0) ? ilogb(sd * gmx) + EOFF : 0;
     const double unit_a = scalbn(1.0, ea - 8 * NS), inv_w = scalbn(1.0, -ew);
+    const double unit_k = scalbn(1.0, ilogb(p.var[0]) + EOFF - 8 * NS);          // kgen_sliced's scale
     if (blockIdx.y == 0) {
 #pragma unroll
         for (int j = 0; j < 4; j++) { p.a_scale[m0 + j] = scalbn(1.0, ea); p.aw_scale[m0 + j] = scalbn(1.0, ew); }
@@ -408,7 +411,8 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     // local restrict-qualified views: the plane stores of row r must not fence the loads of row r + 1 (struct members carry no restrict)
     const int8_t* __restrict__ Ap = p.Ap;
     int8_t* __restrict__ Awp = p.Awp;
-    const double* __restrict__ Kp = p.K;
+    const double* __restrict__ Kf = p.K;
+    const int8_t* __restrict__ Kpl = p.Kp;
     const double* __restrict__ Yp = p.Y;
 #pragma unroll KGP_UNROLL
     for (int r = 0; r < nr; r++) {
@@ -416,11 +420,20 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
         uint32_t wa[NS];
 #pragma unroll
         for (int pl = 0; pl < NS; pl++) wa[pl] = __ldg(reinterpret_cast<const uint32_t*>(Ap + (long long)pl * p.pstride + o));
-        const double4 kk = *reinterpret_cast<const double4*>(Kp + o);
+        double k[4];
+        if (KPL) {
+            uint32_t wk[NS];
+#pragma unroll
+            for (int pl = 0; pl < NS; pl++) wk[pl] = __ldg(reinterpret_cast<const uint32_t*>(Kpl + (long long)pl * p.pstride + o));
+            planes_to_f64x4<NS>(wk, unit_k, k);
+        } else {
+            const double4 kk = *reinterpret_cast<const double4*>(Kf + o);
+            k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
+        }
         const double4 yy = *reinterpret_cast<const double4*>(Yp + o);
         double a[4];
         planes_to_f64x4<NS>(wa, unit_a, a);
-        const double k[4] = {kk.x, kk.y, kk.z, kk.w}, y[4] = {yy.x, yy.y, yy.z, yy.w};
+        const double y[4] = {yy.x, yy.y, yy.z, yy.w};
         const double gmr = sgm[r], gvr = sgv[r];
         uint32_t lo[4], hi[4];
 #pragma unroll
@@ -457,7 +470,7 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
 inline cudaError_t launch_kgrad_planes(int ns, KgradPArgs k, cudaStream_t st) {
     k.rpb = kg_rows_per_block(k.rows, KGP_ROWS);
     const dim3 grid((k.Mp + KGP_THREADS * 4 - 1) / (KGP_THREADS * 4), (k.rows + k.rpb - 1) / k.rpb);
-#define ZIGP_KGP(NSV, DTV) kgrad_planes_kernel<NSV, DTV><<<grid, KGP_THREADS, 0, st>>>(k)
+#define ZIGP_KGP(NSV, DTV) do { if (k.K) kgrad_planes_kernel<NSV, DTV, false><<<grid, KGP_THREADS, 0, st>>>(k); else kgrad_planes_kernel<NSV, DTV, true><<<grid, KGP_THREADS, 0, st>>>(k); } while (0)
 #define ZIGP_KGP_D(NSV)                                  \
     switch (k.D) {                                       \
         case 1: ZIGP_KGP(NSV, 1); break;                 \

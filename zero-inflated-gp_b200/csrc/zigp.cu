@@ -132,6 +132,10 @@ struct zigp_ctx {
     //      latent then runs under the contractions of the other (kgen(g) under A/RA/Y(f), kgrad(g) and the next chunk's kgen under the rank updates).
     //   0 (default) "per latent": latent f on the caller's stream, latent g on the auxiliary one, joined around the likelihood kernel (r1).
     int oz_sched = 0;
+    // ZIGP_OZ_KPLANES=1 (per-latent schedule only): K is not stored as fp64 either -- the gradient kernel rebuilds it from the digit planes the A
+    // product consumed.  Measured at N = 2^22: kgen 32.1 -> 31.1 ms but kgrad 70.1 -> 79.1 ms (seven 4-byte plane loads per 4 elements instead of
+    // one 32-byte load: the kernel is request-bound, not byte-bound), step 565.4 -> 567.8 ms: not the default.
+    bool oz_kplanes = false;
     std::vector<cudaEvent_t> evpool; size_t evnext = 0;
     bool potrf_panel = true;       // diagonal 64-blocks of the Cholesky by the panel kernel (ZIGP_POTRF=0: the column-by-column kernel of r1)
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
@@ -437,7 +441,8 @@ int oz_slice_A(zigp_ctx* c, Latent& L, int rows, int Mp, cudaStream_t st) {
 int chunk_kgen(zigp_ctx* c, int l, const double* theta, const double* X, long long n0, int nvalid, int rows, cudaStream_t st) {
     Latent& L = c->lat[l];
     ProfScope ps(c, PC_KGEN, st);
-    CK(oz::launch_kgen_sliced(c->oz_ns, X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, L.Mp, L.Kb, L.oz_in,
+    const bool kpl = c->oz_pipe && c->oz_kplanes && c->oz_sched == 0;
+    CK(oz::launch_kgen_sliced(c->oz_ns, X, theta + L.off_Z, theta + L.off_ell, theta + L.off_var, n0, nvalid, rows, L.M, c->D, L.Mp, kpl ? nullptr : L.Kb, L.oz_in,
                               (long long)rows * L.Mp, L.oz_rs, st));
     c->launches++;
     return 0;
@@ -519,7 +524,8 @@ int run_point_kernel(zigp_ctx* c, const double* theta, const double* Y, long lon
 int chunk_kgrad(zigp_ctx* c, int l, const double* theta, long long n0, int nvalid, int rows, cudaStream_t st) {
     Latent& L = c->lat[l];
     oz::KgradPArgs k{};
-    k.K = L.Kb; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = (long long)rows * L.Mp;
+    const bool kpl = c->oz_pipe && c->oz_kplanes && c->oz_sched == 0;
+    k.K = kpl ? nullptr : L.Kb; k.Kp = L.oz_in; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = (long long)rows * L.Mp;
     k.gm = L.gm; k.gv = L.gv; k.beta = L.beta; k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows;
     k.Z = theta + L.off_Z; k.M = L.M; k.D = c->D; k.Mp = L.Mp; k.var = theta + L.off_var; k.gvmax = L.oz_gvmax;
     k.partial = L.kg_partial; k.a_scale = L.oz_csA; k.aw_scale = L.oz_csAw;
@@ -1067,6 +1073,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     if (const char* fz = getenv("ZIGP_OZ_FUSE")) c->oz_fuse = atoi(fz);
     if (const char* pz = getenv("ZIGP_OZ_PIPE")) c->oz_pipe = atoi(pz) != 0;
     if (const char* sz = getenv("ZIGP_OZ_SCHED")) c->oz_sched = atoi(sz);
+    if (const char* kz = getenv("ZIGP_OZ_KPLANES")) c->oz_kplanes = atoi(kz) != 0;
     const char* env = getenv("ZIGP_ENGINE");
     if (!(env && std::string(env) == "dmma")) {
         // no silent downgrade: a context that cannot set up its default engine fails to create (ZIGP_ENGINE=dmma asks for the DMMA engine)
@@ -1209,7 +1216,7 @@ int zigp_elbo_grad_dev(zigp_ctx* c, const double* theta, double* out, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     if (c->graph_on && !c->profiling && c->has_data) {
         DeviceGuard guard(c->device);
-        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad + 256 * c->oz_pipe + 512 * c->oz_sched};
+        const zigp_ctx::GraphKey key{theta, out, c->X, c->Y, c->n_local, c->scale, c->engine, c->oz_ns * 16 + c->oz_ns_grad + 256 * c->oz_pipe + 512 * c->oz_sched + 4096 * (c->oz_kplanes ? 1 : 0)};
         if (!c->gexec || memcmp(&key, &c->gkey, sizeof key) != 0) {
             // (re)capture on the context's own stream (the caller's may be the legacy default stream, which cannot be captured)
             if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
