@@ -358,6 +358,7 @@ constexpr int KGP_THREADS = 64;
 #define ZIGP_KGP_UNROLL 2
 #endif
 constexpr int KGP_UNROLL = ZIGP_KGP_UNROLL;
+
 struct KgradPArgs {
     const double* K;                                           // fp64 K, or null: K is rebuilt from its digit planes Kp (sliced under 2^e > 4 var)
     const int8_t* Kp;
@@ -378,27 +379,24 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     __shared__ double sx[KGP_ROWS][DT];
     __shared__ double sgm[KGP_ROWS], sgv[KGP_ROWS];
     const int m0 = blockIdx.x * (KGP_THREADS * 4) + threadIdx.x * 4;
+    const bool live = m0 < p.Mp;                                       // (Mp is a multiple of 64, the CTA covers 256 columns)
     const int r0 = blockIdx.y * p.rpb;
-    const int nr = max(0, min(p.rpb, p.nvalid - r0));
-    const int nrow = min(p.rpb, p.rows - r0);                          // rows of this block inside the padded chunk
-    for (int e = threadIdx.x; e < nr * p.D; e += KGP_THREADS) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0) * p.D + e];
-    for (int e = threadIdx.x; e < nr; e += KGP_THREADS) { sgm[e] = p.gm[r0 + e]; sgv[e] = p.gv[r0 + e]; }
-    __syncthreads();
-    if (m0 >= p.Mp) return;
+    const int nr = max(0, min(p.rpb, p.nvalid - r0));                  // real rows of this block ...
+    const int nrow = min(p.rpb, p.rows - r0);                          // ... and its rows inside the padded chunk
     const double sd = sqrt(p.var[0]);
     const int ea = ilogb(sd) + EOFF;
     const double gmx = __longlong_as_double((long long)p.gvmax[0]);
     const int ew = (gmx > 0.0) ? ilogb(sd * gmx) + EOFF : 0;
     const double unit_a = scalbn(1.0, ea - 8 * NS), inv_w = scalbn(1.0, -ew);
     const double unit_k = scalbn(1.0, ilogb(p.var[0]) + EOFF - 8 * NS);          // kgen_sliced's scale
-    if (blockIdx.y == 0) {
+    if (blockIdx.y == 0 && live) {
 #pragma unroll
         for (int j = 0; j < 4; j++) { p.a_scale[m0 + j] = scalbn(1.0, ea); p.aw_scale[m0 + j] = scalbn(1.0, ew); }
     }
     double z[4][DT], bm[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        bm[j] = p.beta[m0 + j];
+        bm[j] = live ? p.beta[m0 + j] : 0.0;
 #pragma unroll
         for (int d = 0; d < DT; d++) z[j][d] = (d < p.D && m0 + j < p.M) ? p.Z[(long long)(m0 + j) * p.D + d] : 0.0;
     }
@@ -407,52 +405,62 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int d = 0; d < DT; d++) { s1[j][d] = 0.0; q[j][d] = 0.0; }
-    const long long base = (long long)r0 * p.ld + m0;
     // local restrict-qualified views: the plane stores of row r must not fence the loads of row r + 1 (struct members carry no restrict)
     const int8_t* __restrict__ Ap = p.Ap;
     int8_t* __restrict__ Awp = p.Awp;
     const double* __restrict__ Kf = p.K;
     const int8_t* __restrict__ Kpl = p.Kp;
     const double* __restrict__ Yp = p.Y;
+    // rpb may exceed the staging tile (balanced launch: one full wave of CTAs, each with ~rows / ny rows): sub-tiles of KGP_ROWS rows
+    for (int t0 = 0; t0 < nr; t0 += KGP_ROWS) {
+        const int tn = min(KGP_ROWS, nr - t0);
+        if (t0) __syncthreads();
+        for (int e = threadIdx.x; e < tn * p.D; e += KGP_THREADS) sx[e / p.D][e % p.D] = p.X[(p.n0 + r0 + t0) * p.D + e];
+        for (int e = threadIdx.x; e < tn; e += KGP_THREADS) { sgm[e] = p.gm[r0 + t0 + e]; sgv[e] = p.gv[r0 + t0 + e]; }
+        __syncthreads();
+        if (!live) continue;
+        const long long base = (long long)(r0 + t0) * p.ld + m0;
 #pragma unroll KGP_UNROLL
-    for (int r = 0; r < nr; r++) {
-        const long long o = base + (long long)r * p.ld;
-        uint32_t wa[NS];
+        for (int r = 0; r < tn; r++) {
+            const long long o = base + (long long)r * p.ld;
+            uint32_t wa[NS];
 #pragma unroll
-        for (int pl = 0; pl < NS; pl++) wa[pl] = __ldg(reinterpret_cast<const uint32_t*>(Ap + (long long)pl * p.pstride + o));
-        double k[4];
-        if (KPL) {
-            uint32_t wk[NS];
+            for (int pl = 0; pl < NS; pl++) wa[pl] = __ldg(reinterpret_cast<const uint32_t*>(Ap + (long long)pl * p.pstride + o));
+            double k[4];
+            if (KPL) {
+                uint32_t wk[NS];
 #pragma unroll
-            for (int pl = 0; pl < NS; pl++) wk[pl] = __ldg(reinterpret_cast<const uint32_t*>(Kpl + (long long)pl * p.pstride + o));
-            planes_to_f64x4<NS>(wk, unit_k, k);
-        } else {
-            const double4 kk = *reinterpret_cast<const double4*>(Kf + o);
-            k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
-        }
-        const double4 yy = *reinterpret_cast<const double4*>(Yp + o);
-        double a[4];
-        planes_to_f64x4<NS>(wa, unit_a, a);
-        const double y[4] = {yy.x, yy.y, yy.z, yy.w};
-        const double gmr = sgm[r], gvr = sgv[r];
-        uint32_t lo[4], hi[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            slice_bytes<NS>(gvr * a[j] * inv_w, lo[j], hi[j]);
-            const double G = (gmr * bm[j] - 2.0 * gvr * y[j]) * k[j];
-            s0[j] += G;
-            am[j] = fma(gmr, a[j], am[j]);
-#pragma unroll
-            for (int d = 0; d < DT; d++) {
-                if (d < p.D) { const double df = sx[r][d] - z[j][d]; s1[j][d] = fma(G, df, s1[j][d]); q[j][d] = fma(G * df, df, q[j][d]); }
+                for (int pl = 0; pl < NS; pl++) wk[pl] = __ldg(reinterpret_cast<const uint32_t*>(Kpl + (long long)pl * p.pstride + o));
+                planes_to_f64x4<NS>(wk, unit_k, k);
+            } else {
+                const double4 kk = *reinterpret_cast<const double4*>(Kf + o);
+                k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
             }
-        }
+            const double4 yy = *reinterpret_cast<const double4*>(Yp + o);
+            double a[4];
+            planes_to_f64x4<NS>(wa, unit_a, a);
+            const double y[4] = {yy.x, yy.y, yy.z, yy.w};
+            const double gmr = sgm[r], gvr = sgv[r];
+            uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(Awp + (long long)pl * p.pstride + o) = plane_word4<NS>(pl, lo, hi);
+            for (int j = 0; j < 4; j++) {
+                slice_bytes<NS>(gvr * a[j] * inv_w, lo[j], hi[j]);
+                const double G = (gmr * bm[j] - 2.0 * gvr * y[j]) * k[j];
+                s0[j] += G;
+                am[j] = fma(gmr, a[j], am[j]);
+#pragma unroll
+                for (int d = 0; d < DT; d++) {
+                    if (d < p.D) { const double df = sx[r][d] - z[j][d]; s1[j][d] = fma(G, df, s1[j][d]); q[j][d] = fma(G * df, df, q[j][d]); }
+                }
+            }
+#pragma unroll
+            for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(Awp + (long long)pl * p.pstride + o) = plane_word4<NS>(pl, lo, hi);
+        }
     }
+    if (!live) return;
     for (int r = nr; r < nrow; r++) {                                  // padding rows of the chunk: gv * A = 0 -> all-zero digits
 #pragma unroll
-        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(p.Awp + (long long)pl * p.pstride + base + (long long)r * p.ld) = 0u;
+        for (int pl = 0; pl < NS; pl++) *reinterpret_cast<uint32_t*>(p.Awp + (long long)pl * p.pstride + (long long)(r0 + r) * p.ld + m0) = 0u;
     }
     if (nr <= 0) return;
     double* out = p.partial + (long long)blockIdx.y * (2 + 2 * p.D) * p.Mp + m0;
@@ -467,10 +475,38 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     }
 }
 
-inline cudaError_t launch_kgrad_planes(int ns, KgradPArgs k, cudaStream_t st) {
+// Launch shape.  Small chunks: 16-row blocks (latency).  Large chunks: ONE balanced wave -- the kernel is a stream over 2 GB per 65536-row chunk
+// and 2048 blocks of 128 rows were 2.31 waves of the 148 x 6 resident CTAs (the third, 31 %-full wave cost ~20 %); instead the rows are dealt
+// evenly to ny = (resident CTAs) / (column groups) row groups, every CTA resident from the start and finishing together.  ny never exceeds the
+// slot count the context allocated (max_slots; 0 = plain tiling).
+template <int NS, int DT, bool KPL>
+inline int kgp_resident_ctas() {
+    static int cached[16] = {0};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) dev = 0;
+    if (!cached[dev]) {
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kgrad_planes_kernel<NS, DT, KPL>, KGP_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+        cached[dev] = per_sm * sms;
+    }
+    return cached[dev];
+}
+template <int NS, int DT, bool KPL>
+inline void launch_kgrad_planes_t(KgradPArgs k, int max_slots, cudaStream_t st) {
+    const int gx = (k.Mp + KGP_THREADS * 4 - 1) / (KGP_THREADS * 4);
     k.rpb = kg_rows_per_block(k.rows, KGP_ROWS);
-    const dim3 grid((k.Mp + KGP_THREADS * 4 - 1) / (KGP_THREADS * 4), (k.rows + k.rpb - 1) / k.rpb);
-#define ZIGP_KGP(NSV, DTV) do { if (k.K) kgrad_planes_kernel<NSV, DTV, false><<<grid, KGP_THREADS, 0, st>>>(k); else kgrad_planes_kernel<NSV, DTV, true><<<grid, KGP_THREADS, 0, st>>>(k); } while (0)
+    if (k.rows > KG_SMALL_LIMIT && max_slots > 0) {
+        const int ny = std::max(1, std::min(kgp_resident_ctas<NS, DT, KPL>() / gx, max_slots));
+        const int rpb = (k.rows + ny - 1) / ny;
+        if (rpb >= KGP_ROWS) k.rpb = rpb;                              // (fewer rows per CTA than the plain tiling: keep the plain tiling)
+    }
+    const dim3 grid(gx, (k.rows + k.rpb - 1) / k.rpb);
+    kgrad_planes_kernel<NS, DT, KPL><<<grid, KGP_THREADS, 0, st>>>(k);
+}
+
+inline cudaError_t launch_kgrad_planes(int ns, KgradPArgs k, int max_slots, cudaStream_t st) {
+#define ZIGP_KGP(NSV, DTV) do { if (k.K) launch_kgrad_planes_t<NSV, DTV, false>(k, max_slots, st); else launch_kgrad_planes_t<NSV, DTV, true>(k, max_slots, st); } while (0)
 #define ZIGP_KGP_D(NSV)                                  \
     switch (k.D) {                                       \
         case 1: ZIGP_KGP(NSV, 1); break;                 \

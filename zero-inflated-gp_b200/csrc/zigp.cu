@@ -136,6 +136,8 @@ struct zigp_ctx {
     // product consumed.  Measured at N = 2^22: kgen 32.1 -> 31.1 ms but kgrad 70.1 -> 79.1 ms (seven 4-byte plane loads per 4 elements instead of
     // one 32-byte load: the kernel is request-bound, not byte-bound), step 565.4 -> 567.8 ms: not the default.
     bool oz_kplanes = false;
+    // gradient-sum kernel of the planes pipeline on large chunks: one balanced wave of CTAs (ZIGP_KG_BALANCED=0: 128-row blocks, 2.3 waves)
+    bool kg_balanced = true;
     std::vector<cudaEvent_t> evpool; size_t evnext = 0;
     bool potrf_panel = true;       // diagonal 64-blocks of the Cholesky by the panel kernel (ZIGP_POTRF=0: the column-by-column kernel of r1)
     int oz_fuse = 1;               // 0: A is re-sliced by separate kernels, 1: row planes from the A product's epilogue, 2: and the transposed planes (ZIGP_OZ_FUSE)
@@ -530,7 +532,7 @@ int chunk_kgrad(zigp_ctx* c, int l, const double* theta, long long n0, int nvali
     k.Z = theta + L.off_Z; k.M = L.M; k.D = c->D; k.Mp = L.Mp; k.var = theta + L.off_var; k.gvmax = L.oz_gvmax;
     k.partial = L.kg_partial; k.a_scale = L.oz_csA; k.aw_scale = L.oz_csAw;
     ProfScope ps(c, PC_KGRAD, st);
-    CK(oz::launch_kgrad_planes(c->oz_ns, k, st));
+    CK(oz::launch_kgrad_planes(c->oz_ns, k, c->kg_balanced ? c->kg_slots : 0, st));
     c->launches++;
     return 0;
 }
@@ -1074,6 +1076,7 @@ int zigp_create_ex(zigp_ctx** out, int device, int Mf, int Mg, int D, double jit
     if (const char* pz = getenv("ZIGP_OZ_PIPE")) c->oz_pipe = atoi(pz) != 0;
     if (const char* sz = getenv("ZIGP_OZ_SCHED")) c->oz_sched = atoi(sz);
     if (const char* kz = getenv("ZIGP_OZ_KPLANES")) c->oz_kplanes = atoi(kz) != 0;
+    if (const char* kb = getenv("ZIGP_KG_BALANCED")) c->kg_balanced = atoi(kb) != 0;
     const char* env = getenv("ZIGP_ENGINE");
     if (!(env && std::string(env) == "dmma")) {
         // no silent downgrade: a context that cannot set up its default engine fails to create (ZIGP_ENGINE=dmma asks for the DMMA engine)
