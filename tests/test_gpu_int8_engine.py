@@ -95,6 +95,35 @@ def test_planes_pipeline_equals_the_r1_pipeline(monkeypatch):
         assert np.linalg.norm(ga[k] - gb[k]) <= 1e-10 * np.linalg.norm(gb[k]) + 1e-13 * full, (k, np.linalg.norm(ga[k] - gb[k]) / np.linalg.norm(gb[k]))
 
 
+@pytest.mark.parametrize("M,chunk", [(192, 65536), (512, 65536), (1024, 65536), (320, 147456)])
+def test_balanced_gradient_launch_equals_the_plain_tiling(monkeypatch, M, chunk):
+    """ZIGP_KG_BALANCED=1 (default: kgrad_planes_kernel as ONE wave of CTAs, the chunk's rows dealt evenly to (resident CTAs) / (column groups)
+    row groups, sub-tiles of 128 rows inside a CTA) against =0 (128-row blocks): only the order of the per-column sums changes.  Same ELBO bit
+    for bit (forward path untouched), packed gradient to 1e-12 of its norm.  Ragged problems: a full chunk plus a last chunk that is above the
+    small-chunk limit (16384 rows) but far from full, so the balanced row count is not a multiple of anything; 1, 2, 4 and 2 column groups."""
+    N, D = chunk + 23_457, 3
+    X, Y = synth.make_data(N, D, 33)
+    X[:300] += 2.5
+    p = synth.make_params(M, M, D, 33)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZIGP_KG_BALANCED", mode)
+        m = synth.build_model(X, Y, p, engine="int8", chunk_rows=chunk)
+        m.build_likelihood()
+        outs[mode] = m._last_out.cpu().numpy()
+        del m
+    a, b = outs["1"], outs["0"]
+    assert np.all(np.isfinite(a)) and a[3] == 0
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    ga, gb = synth.unpack_grad(a[4:], M, M, D), synth.unpack_grad(b[4:], M, M, D)
+    full = np.linalg.norm(b[4:])
+    for k in gb:
+        assert np.linalg.norm(ga[k] - gb[k]) <= 1e-12 * np.linalg.norm(gb[k]) + 1e-14 * full, (k, np.linalg.norm(ga[k] - gb[k]) / np.linalg.norm(gb[k]))
+    # the q_sqrt gradients come from the rank update over the digit planes the kernel writes: those planes must not depend on the launch shape
+    for k in ("u_fs_sqrt", "u_gs_sqrt"):
+        assert np.array_equal(ga[k], gb[k]), k
+
+
 def test_stream_schedules_are_bit_identical(monkeypatch):
     """ZIGP_OZ_SCHED=2 (default: chunk-pipelined -- contractions on a high-priority stream, Kmn tiles / likelihood / gradient sums on a second
     stream one chunk ahead / behind, doubled hand-over buffers, event edges) and =1 (same two roles without the doubling) only change WHEN kernels
