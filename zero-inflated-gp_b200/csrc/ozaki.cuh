@@ -360,8 +360,8 @@ constexpr int KGP_THREADS = 64;
 constexpr int KGP_UNROLL = ZIGP_KGP_UNROLL;
 
 struct KgradPArgs {
-    const double* K;                                           // fp64 K, or null: K is rebuilt from its digit planes Kp (sliced under 2^e > 4 var)
-    const int8_t* Kp;
+    const double* K;                                           // fp64 K, or null: K is recomputed from X, Z, ell, var (ZIGP_OZ_KPLANES mode)
+    const double* ell;
     const double* Y; long long ld;
     const int8_t* Ap; int8_t* Awp; long long pstride;          // planes of A (in) and of gv * A (out), plane stride in bytes
     const double* gm; const double* gv; const double* beta;
@@ -388,7 +388,10 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     const double gmx = __longlong_as_double((long long)p.gvmax[0]);
     const int ew = (gmx > 0.0) ? ilogb(sd * gmx) + EOFF : 0;
     const double unit_a = scalbn(1.0, ea - 8 * NS), inv_w = scalbn(1.0, -ew);
-    const double unit_k = scalbn(1.0, ilogb(p.var[0]) + EOFF - 8 * NS);          // kgen_sliced's scale
+    const double kvar = p.var[0];
+    double il[DT];
+#pragma unroll
+    for (int d = 0; d < DT; d++) il[d] = (KPL && d < p.D) ? 1.0 / p.ell[d] : 0.0;
     if (blockIdx.y == 0 && live) {
 #pragma unroll
         for (int j = 0; j < 4; j++) { p.a_scale[m0 + j] = scalbn(1.0, ea); p.aw_scale[m0 + j] = scalbn(1.0, ew); }
@@ -409,7 +412,6 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
     const int8_t* __restrict__ Ap = p.Ap;
     int8_t* __restrict__ Awp = p.Awp;
     const double* __restrict__ Kf = p.K;
-    const int8_t* __restrict__ Kpl = p.Kp;
     const double* __restrict__ Yp = p.Y;
     // rpb may exceed the staging tile (balanced launch: one full wave of CTAs, each with ~rows / ny rows): sub-tiles of KGP_ROWS rows
     for (int t0 = 0; t0 < nr; t0 += KGP_ROWS) {
@@ -428,10 +430,17 @@ __global__ void __launch_bounds__(KGP_THREADS, (DT <= 4 ? ZIGP_KGP_MINB : 1)) kg
             for (int pl = 0; pl < NS; pl++) wa[pl] = __ldg(reinterpret_cast<const uint32_t*>(Ap + (long long)pl * p.pstride + o));
             double k[4];
             if (KPL) {
-                uint32_t wk[NS];
+                // K recomputed from x and z with kgen_sliced_kernel's own arithmetic (same operations in the same order: bit-identical to the
+                // tile the forward products were sliced from); rows r < nr are real points
 #pragma unroll
-                for (int pl = 0; pl < NS; pl++) wk[pl] = __ldg(reinterpret_cast<const uint32_t*>(Kpl + (long long)pl * p.pstride + o));
-                planes_to_f64x4<NS>(wk, unit_k, k);
+                for (int j = 0; j < 4; j++) {
+                    double r2 = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DT; d++) {
+                        if (d < p.D) { const double t = (sx[r][d] - z[j][d]) * il[d]; r2 = fma(t, t, r2); }     // (d >= D adds fma(0, 0, r2) in kgen_sliced: the same value)
+                    }
+                    k[j] = (m0 + j < p.M) ? kvar * exp(-0.5 * r2) : 0.0;
+                }
             } else {
                 const double4 kk = *reinterpret_cast<const double4*>(Kf + o);
                 k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;

@@ -132,9 +132,11 @@ struct zigp_ctx {
     //      latent then runs under the contractions of the other (kgen(g) under A/RA/Y(f), kgrad(g) and the next chunk's kgen under the rank updates).
     //   0 (default) "per latent": latent f on the caller's stream, latent g on the auxiliary one, joined around the likelihood kernel (r1).
     int oz_sched = 0;
-    // ZIGP_OZ_KPLANES=1 (per-latent schedule only): K is not stored as fp64 either -- the gradient kernel rebuilds it from the digit planes the A
-    // product consumed.  Measured at N = 2^22: kgen 32.1 -> 31.1 ms but kgrad 70.1 -> 79.1 ms (seven 4-byte plane loads per 4 elements instead of
-    // one 32-byte load: the kernel is request-bound, not byte-bound), step 565.4 -> 567.8 ms: not the default.
+    // ZIGP_OZ_KPLANES=1 (per-latent schedule only): K is not stored as fp64 -- the Kmn kernel writes only the digit planes and the gradient kernel
+    // recomputes K from X, Z, ell, var with the same arithmetic (bit-identical tile).  A first form that rebuilt K from the digit planes instead
+    // measured kgen 32.1 -> 31.1 ms but kgrad 70.1 -> 79.1 ms at N = 2^22 (seven more 4-byte loads per thread and row: request-bound).
+    // The recompute form (profiles/ab_kplanes_r02.txt): kgen 33.4 -> 31.6 ms, kgrad 56.7 -> 84.1 ms (one fp64 exp per element makes the
+    // gradient kernel ALU-bound), step 574.4 -> 590.5 ms.  Parity-green (72 tests with the switch on), NOT the default.
     bool oz_kplanes = false;
     // gradient-sum kernel of the planes pipeline on large chunks: one balanced wave of CTAs (ZIGP_KG_BALANCED=0: 128-row blocks, 2.3 waves)
     bool kg_balanced = true;
@@ -527,7 +529,7 @@ int chunk_kgrad(zigp_ctx* c, int l, const double* theta, long long n0, int nvali
     Latent& L = c->lat[l];
     oz::KgradPArgs k{};
     const bool kpl = c->oz_pipe && c->oz_kplanes && c->oz_sched == 0;
-    k.K = kpl ? nullptr : L.Kb; k.Kp = L.oz_in; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = (long long)rows * L.Mp;
+    k.K = kpl ? nullptr : L.Kb; k.ell = theta + L.off_ell; k.Y = L.RAb; k.ld = L.Mp; k.Ap = L.oz_inA; k.Awp = L.oz_colAw; k.pstride = (long long)rows * L.Mp;
     k.gm = L.gm; k.gv = L.gv; k.beta = L.beta; k.X = c->X; k.n0 = n0; k.nvalid = nvalid; k.rows = rows;
     k.Z = theta + L.off_Z; k.M = L.M; k.D = c->D; k.Mp = L.Mp; k.var = theta + L.off_var; k.gvmax = L.oz_gvmax;
     k.partial = L.kg_partial; k.a_scale = L.oz_csA; k.aw_scale = L.oz_csAw;
