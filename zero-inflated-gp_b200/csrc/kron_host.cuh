@@ -60,11 +60,31 @@ int kron_mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st
     return 0;
 }
 
+// a factor whose product chains run as the fused kernels of kron_fused.cuh
+inline bool kron_factor_fused(const zigp_ctx* c, const KFactor& F) { return c->kron_fused && F.Mp == KF_M && F.D >= 1 && F.D <= KF_MAXD; }
+
+KronFusedArgs kron_fused_args(zigp_ctx* c, KFactor& F, const double* theta, const double* X, long long n0, int nvalid, int rows) {
+    KronFusedArgs a{};
+    a.T = F.T; a.Z = theta + F.off_Z; a.ell = theta + F.off_ell; a.var = theta + F.off_var; a.M = F.M; a.D = F.D;
+    a.X = X; a.xstride = c->Ds + c->Dt; a.xoff = F.xoff; a.n0 = n0; a.nvalid = nvalid; a.rows = rows;
+    a.K = F.Kb; a.A = F.Ab; a.U = F.Ub; a.sq = F.sq;
+    return a;
+}
+
 int kron_chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X, long long n0, int nvalid, int rows, cudaStream_t st) {
     KLatent& L = c->klat[l];
     const int xstride = c->Ds + c->Dt;
     for (int p = 0; p < 2; p++) {
         KFactor& F = L.f[p];
+        if (kron_factor_fused(c, F)) {
+            // k (computed) -> a = k T^T (+ |a|^2) -> u = a T (+ u^2 for the time factor): one launch, K / A / U written once
+            KronFusedArgs a = kron_fused_args(c, F, theta, X, n0, nvalid, rows);
+            a.U2 = (p == 1) ? L.W2 : nullptr;
+            ProfScope ps(c, PC_GEMM, st);
+            CK(launch_kron_chain<0>(a, c->n_sms, 0, st));
+            c->launches++;
+            continue;
+        }
         dim3 gk(F.Mp / 32, rows / 64);
         {
             ProfScope ps(c, PC_KGEN, st);
@@ -123,6 +143,15 @@ int kron_chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, i
         KFactor& F = L.f[p];
         KFactor& O = L.f[1 - p];
         RUN(kron_nt(c, F.Ab, F.Mp, F.Mp, F.Vb, F.Mp, F.Mp, F.F_splits, L.nsplit, rows, st));                                  // FT += A^T V
+        if (kron_factor_fused(c, F)) {
+            // v -> T v -> K^-1 v -> kernel-gradient sums: one launch, no tmp / KV arrays
+            KronFusedArgs a = kron_fused_args(c, F, theta, c->X, n0, nvalid, rows);
+            a.V = F.Vb; a.gv = L.gv; a.po = O.p; a.partial = F.kg_partial;
+            ProfScope ps(c, PC_GEMM, st);
+            CK(launch_kron_chain<1>(a, c->n_sms, c->kg_slots, st));
+            c->launches++;
+            continue;
+        }
         RUN(kron_gemm(c, F.Vb, F.Mp, F.T, F.Mp, F.tmp, F.Mp, rows, F.Mp, F.Mp, TRI_LOWER, nullptr, nullptr, st));             // T v
         RUN(kron_gemm(c, F.tmp, F.Mp, F.Tt, F.Mp, F.KVb, F.Mp, rows, F.Mp, F.Mp, TRI_UPPER, nullptr, nullptr, st));           // K^-1 v
         KronKgradArgs k{};

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include "kron.cuh"
+#include "kron_fused.cuh"
 #include "ozaki.cuh"
 
 using namespace zigp;
@@ -138,6 +139,9 @@ struct zigp_ctx {
     // The recompute form (profiles/ab_kplanes_r02.txt): kgen 33.4 -> 31.6 ms, kgrad 56.7 -> 84.1 ms (one fp64 exp per element makes the
     // gradient kernel ALU-bound), step 574.4 -> 590.5 ms.  Parity-green (72 tests with the switch on), NOT the default.
     bool oz_kplanes = false;
+    // Kronecker variant: factors padded to 64 run their forward / backward product chains as one fused kernel each (kron_fused.cuh);
+    // ZIGP_KRON_FUSED=0: the unfused launches (any factor size)
+    bool kron_fused = true; int n_sms = 0;
     // gradient-sum kernel of the planes pipeline on large chunks: one balanced wave of CTAs (ZIGP_KG_BALANCED=0: 128-row blocks, 2.3 waves)
     bool kg_balanced = true;
     std::vector<cudaEvent_t> evpool; size_t evnext = 0;
@@ -1122,6 +1126,8 @@ int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g
     c->chunk = rup(chunk, 512);
     const int Ms[2] = {Ms_f, Ms_g}, Mt[2] = {Mt_f, Mt_g};
     { int r = kron_alloc(c, Ms, Mt); if (r) return fail(r); }
+    if (const char* kf = getenv("ZIGP_KRON_FUSED")) c->kron_fused = atoi(kf) != 0;
+    if (cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->n_sms < 1) { c->err = "cudaDeviceGetAttribute(multiProcessorCount) failed"; return fail(ZIGP_ECUDA); }
     if (const char* pz = getenv("ZIGP_POTRF")) c->potrf_panel = atoi(pz) != 0;
     if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(potrf_diag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess) {
