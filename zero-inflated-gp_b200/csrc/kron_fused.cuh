@@ -221,6 +221,210 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
     }
 }
 
+// ---- the Ms x Mt products between the factors (both padded to 64) --------------------------------------------------------------------
+// 8 warps per CTA here (warp tile 16 x 32, FM = 2 row fragments): the kernels hold two accumulator sets or the u fragments next to one, and
+// with 4 warps (FM = 4) that took 255 registers and 2 x 4 warps per SM -- latency-bound (level 2 was 4 % SLOWER than the unfused launches it
+// replaced, profiles/ab_kron_fused_r02.txt); 2 CTAs x 8 warps fit in 128 registers per thread.
+constexpr int KM_THREADS = 256;
+constexpr int KM_FM = 2;                 // row fragments per warp; warp (wm, wn) owns rows [16 wm, 16 wm + 16) x columns [32 wn, 32 wn + 32)
+
+// acc[i][j][e] = sum_k f(sIn[row][k]) * W[col][k], all 64 k; f = identity or square (the w^2 / u^2 operands are never materialised);
+// WT = false: W[c][k] = sW[c][k];  WT = true: W[c][k] = sW[k][c] (the transposed factor read from the same copy, as in kf_tri_product)
+template <bool WT, bool SQ>
+__device__ __forceinline__ void km_full_product(const double* sIn, const double* sW, int wm, int wn, int fr, int fk, double (&acc)[KM_FM][4][2]) {
+#pragma unroll
+    for (int i = 0; i < KM_FM; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const double* cIn = sIn + (wm * 8 * KM_FM + fr) * KF_STR + fk;
+    const double* cW = WT ? sW + fk * KF_STR + wn * 32 + fr : sW + (wn * 32 + fr) * KF_STR + fk;
+    constexpr int WJ = WT ? 8 : 8 * KF_STR, WK = WT ? KF_STR : 1;
+#pragma unroll
+    for (int kk = 0; kk < KF_M; kk += 4) {
+        double a[KM_FM], b[4];
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++) { const double v = cIn[i * 8 * KF_STR + kk]; a[i] = SQ ? v * v : v; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = cW[j * WJ + kk * WK];
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+struct KronMidArgs {
+    const double* Q; const double* S2;                   // 64 x 64 row-major [i_space][j_time]
+    const double* Us; const double* Ut;                  // u (space), w (time): [rows][64]
+    double* QW; double* SW;                              // forward: out ; backward: in
+    int rows;
+    // forward
+    const double* sqs; const double* sqt; const double* var_s; const double* var_t;
+    double* mean; double* vr; double* ps; double* pt;    // (backward reads ps, pt)
+    // backward
+    const double* Ks; const double* Kt; const double* gm; const double* gv;
+    double* Vs; double* Vt; double* P1; double* P2;
+};
+
+constexpr size_t KF_MID_SMEM = (size_t)(3 * KF_M * KF_STR + 4 * KF_ROWS) * sizeof(double);
+
+template <int THREADS>
+__device__ __forceinline__ void km_load64x64(double* s, const double* __restrict__ g, int tid) {
+    for (int c = tid; c < 64 * (KF_M / 2); c += THREADS) {
+        const int r = c / (KF_M / 2), q = c % (KF_M / 2);
+        cp_async16(s + r * KF_STR + q * 2, g + (long long)r * KF_M + q * 2);
+    }
+}
+
+// forward: QW = w Q^T, SW = w^2 S2^T, mean = u . QW, var = vs vt - ps pt + u^2 . SW   (replaces 2 x gemm_tn_f64 + kron_moments_kernel; W2 is not read)
+__global__ void __launch_bounds__(KM_THREADS, 2) kron_mid_fwd_kernel(const KronMidArgs p) {
+    extern __shared__ __align__(16) double kf_smem[];
+    double* sQ = kf_smem;
+    double* sS2 = sQ + KF_M * KF_STR;
+    double* sIn = sS2 + KF_M * KF_STR;
+    double* sred = sIn + KF_ROWS * KF_STR;               // [2 column halves][2: mean, t3][KF_ROWS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
+    km_load64x64<KM_THREADS>(sQ, p.Q, tid);
+    km_load64x64<KM_THREADS>(sS2, p.S2, tid);
+    cp_async_commit();
+    const double vsvt = p.var_s[0] * p.var_t[0];
+    const int ntiles = p.rows / KF_ROWS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * KF_ROWS;
+        if (tile != (int)blockIdx.x) __syncthreads();                 // the previous tile's products and row sums are done
+        km_load64x64<KM_THREADS>(sIn, p.Ut + (long long)row0 * KF_M, tid);
+        cp_async_commit();
+        // u fragments of this thread (same element positions as its accumulators), requested before the wait
+        double2 uf[KM_FM][4];
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                uf[i][j] = *reinterpret_cast<const double2*>(p.Us + (long long)(row0 + wm * 8 * KM_FM + i * 8 + fr) * KF_M + wn * 32 + j * 8 + 2 * fk);
+        cp_async_wait<0>();
+        __syncthreads();
+        double acc[KM_FM][4][2], pm[KM_FM], pt3[KM_FM];
+        km_full_product<false, false>(sIn, sQ, wm, wn, fr, fk, acc);
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++) {
+            const long long o = (long long)(row0 + wm * 8 * KM_FM + i * 8 + fr) * KF_M + wn * 32 + 2 * fk;
+            double m = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                *reinterpret_cast<double2*>(p.QW + o + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+                m = fma(uf[i][j].x, acc[i][j][0], m); m = fma(uf[i][j].y, acc[i][j][1], m);
+            }
+            pm[i] = m;
+        }
+        km_full_product<false, true>(sIn, sS2, wm, wn, fr, fk, acc);
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++) {
+            const long long o = (long long)(row0 + wm * 8 * KM_FM + i * 8 + fr) * KF_M + wn * 32 + 2 * fk;
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                *reinterpret_cast<double2*>(p.SW + o + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+                t = fma(uf[i][j].x * uf[i][j].x, acc[i][j][0], t); t = fma(uf[i][j].y * uf[i][j].y, acc[i][j][1], t);
+            }
+            pt3[i] = t;
+        }
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++) {
+            double m = pm[i], t = pt3[i];
+            m += __shfl_xor_sync(0xffffffffu, m, 1); m += __shfl_xor_sync(0xffffffffu, m, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2);
+            if (fk == 0) {
+                const int r = wm * 8 * KM_FM + i * 8 + fr;
+                sred[(wn * 2 + 0) * KF_ROWS + r] = m; sred[(wn * 2 + 1) * KF_ROWS + r] = t;
+            }
+        }
+        __syncthreads();
+        if (tid < KF_ROWS) {
+            const int r = row0 + tid;
+            const double a = p.sqs[r], b = p.sqt[r];
+            p.mean[r] = sred[0 * KF_ROWS + tid] + sred[2 * KF_ROWS + tid];
+            p.vr[r] = vsvt - a * b + (sred[1 * KF_ROWS + tid] + sred[3 * KF_ROWS + tid]);
+            p.ps[r] = a; p.pt[r] = b;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// backward: QtU = u Q, StU2 = u^2 S2 (never stored), Vt = gm QtU + 2 gv w StU2 - gv ps Kt, Vs = gm QW + 2 gv u SW - gv pt Ks, P1 = gm u, P2 = gv u^2
+// (replaces kron_bwd_s_kernel + 2 x gemm_tn_f64 + kron_bwd_t_kernel and the U2 / QtU / StU2 arrays)
+__global__ void __launch_bounds__(KM_THREADS, 2) kron_mid_bwd_kernel(const KronMidArgs p) {
+    extern __shared__ __align__(16) double kf_smem[];
+    double* sQ = kf_smem;
+    double* sS2 = sQ + KF_M * KF_STR;
+    double* sIn = sS2 + KF_M * KF_STR;
+    double* sgm = sIn + KF_ROWS * KF_STR;
+    double* sgv = sgm + KF_ROWS;
+    double* sps = sgv + KF_ROWS;
+    double* spt = sps + KF_ROWS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 3, wn = warp >> 2, fr = lane >> 2, fk = lane & 3;
+    km_load64x64<KM_THREADS>(sQ, p.Q, tid);
+    km_load64x64<KM_THREADS>(sS2, p.S2, tid);
+    cp_async_commit();
+    const int ntiles = p.rows / KF_ROWS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * KF_ROWS;
+        if (tile != (int)blockIdx.x) __syncthreads();
+        km_load64x64<KM_THREADS>(sIn, p.Us + (long long)row0 * KF_M, tid);
+        cp_async_commit();
+        if (tid < KF_ROWS) { sgm[tid] = p.gm[row0 + tid]; sgv[tid] = p.gv[row0 + tid]; sps[tid] = p.ps[row0 + tid]; spt[tid] = p.pt[row0 + tid]; }
+        cp_async_wait<0>();
+        __syncthreads();
+        // time side, fragment layout: both products first (StU2 stays in registers), then one pass over w, Kt -> Vt
+        double acc1[KM_FM][4][2], acc2[KM_FM][4][2];
+        km_full_product<true, false>(sIn, sQ, wm, wn, fr, fk, acc1);
+        km_full_product<true, true>(sIn, sS2, wm, wn, fr, fk, acc2);
+#pragma unroll
+        for (int i = 0; i < KM_FM; i++) {
+            const int r = wm * 8 * KM_FM + i * 8 + fr;
+            const long long o = (long long)(row0 + r) * KF_M + wn * 32 + 2 * fk;
+            const double g1 = sgm[r], g2 = sgv[r], gp = g2 * sps[r];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double2 w = *reinterpret_cast<const double2*>(p.Ut + o + j * 8);
+                const double2 k = *reinterpret_cast<const double2*>(p.Kt + o + j * 8);
+                *reinterpret_cast<double2*>(p.Vt + o + j * 8) = make_double2(g1 * acc1[i][j][0] + 2.0 * g2 * w.x * acc2[i][j][0] - gp * k.x,
+                                                                            g1 * acc1[i][j][1] + 2.0 * g2 * w.y * acc2[i][j][1] - gp * k.y);
+            }
+        }
+        // space side, one column per thread over 16 rows: coalesced rows of QW, SW, Ks in, Vs, P1, P2 out; u from the tile in shared memory
+        const int m = tid & 63, rq = tid >> 6;
+#pragma unroll 4
+        for (int rr = 0; rr < 16; rr++) {
+            const int r = rq * 16 + rr;
+            const long long e = (long long)(row0 + r) * KF_M + m;
+            const double u = sIn[r * KF_STR + m], g1 = sgm[r], g2 = sgv[r];
+            p.Vs[e] = g1 * p.QW[e] + 2.0 * g2 * u * p.SW[e] - g2 * spt[r] * p.Ks[e];
+            p.P1[e] = g1 * u; p.P2[e] = g2 * u * u;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+inline cudaError_t launch_kron_mid(bool backward, const KronMidArgs& a, int n_sms, cudaStream_t st) {
+    const int ntiles = a.rows / KF_ROWS;
+    const int grid = std::min(ntiles, 2 * n_sms);
+    if (grid < 1) return cudaSuccess;
+    static bool attr_done[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(dev >= 0 && dev < MAX_DEVICES && attr_done[dev])) {
+        cudaError_t e = cudaFuncSetAttribute(kron_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_MID_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kron_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KF_MID_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < MAX_DEVICES) attr_done[dev] = true;
+    }
+    if (backward) kron_mid_bwd_kernel<<<grid, KM_THREADS, KF_MID_SMEM, st>>>(a);
+    else kron_mid_fwd_kernel<<<grid, KM_THREADS, KF_MID_SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
 constexpr size_t kf_smem_bytes(int dt) {
     return (size_t)(2 * KF_M * KF_STR + KF_ROWS * dt + KF_ROWS + 2 * (1 + 2 * dt) * KF_M) * sizeof(double);
 }

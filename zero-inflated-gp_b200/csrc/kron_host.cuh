@@ -61,7 +61,19 @@ int kron_mstage_forward(zigp_ctx* c, int l, const double* theta, cudaStream_t st
 }
 
 // a factor whose product chains run as the fused kernels of kron_fused.cuh
-inline bool kron_factor_fused(const zigp_ctx* c, const KFactor& F) { return c->kron_fused && F.Mp == KF_M && F.D >= 1 && F.D <= KF_MAXD; }
+inline bool kron_factor_fused(const zigp_ctx* c, const KFactor& F) { return c->kron_fused >= 1 && F.Mp == KF_M && F.D >= 1 && F.D <= KF_MAXD; }
+// a latent whose Ms x Mt products run inside kron_mid_fwd_kernel / kron_mid_bwd_kernel (both factors padded to 64)
+inline bool kron_mid_fused(const zigp_ctx* c, const KLatent& L) { return c->kron_fused >= 2 && L.f[0].Mp == KF_M && L.f[1].Mp == KF_M; }
+
+KronMidArgs kron_mid_args(KLatent& L, const double* theta, int rows) {
+    KFactor &S = L.f[0], &T = L.f[1];
+    KronMidArgs a{};
+    a.Q = L.Q; a.S2 = L.S2; a.Us = S.Ub; a.Ut = T.Ub; a.QW = L.QW; a.SW = L.SW; a.rows = rows;
+    a.sqs = S.sq; a.sqt = T.sq; a.var_s = theta + S.off_var; a.var_t = theta + T.off_var;
+    a.mean = L.mean; a.vr = L.vr; a.ps = S.p; a.pt = T.p;
+    a.Ks = S.Kb; a.Kt = T.Kb; a.gm = L.gm; a.gv = L.gv; a.Vs = S.Vb; a.Vt = T.Vb; a.P1 = L.P1; a.P2 = L.P2;
+    return a;
+}
 
 KronFusedArgs kron_fused_args(zigp_ctx* c, KFactor& F, const double* theta, const double* X, long long n0, int nvalid, int rows) {
     KronFusedArgs a{};
@@ -95,6 +107,13 @@ int kron_chunk_forward(zigp_ctx* c, int l, const double* theta, const double* X,
         RUN(kron_gemm(c, F.Ab, F.Mp, F.Tt, F.Mp, F.Ub, F.Mp, rows, F.Mp, F.Mp, TRI_UPPER, nullptr, p == 1 ? L.W2 : nullptr, st));  // u = T^T a
     }
     KFactor &S = L.f[0], &T = L.f[1];
+    if (kron_mid_fused(c, L)) {
+        // QW = W Q^T, SW = W^2 S2^T and the moments in one launch (w^2 formed on the fly)
+        ProfScope ps(c, PC_GEMM, st);
+        CK(launch_kron_mid(false, kron_mid_args(L, theta, rows), c->n_sms, st));
+        c->launches++;
+        return 0;
+    }
     RUN(kron_gemm(c, T.Ub, T.Mp, L.Q, T.Mp, L.QW, S.Mp, rows, S.Mp, T.Mp, TRI_FULL, nullptr, nullptr, st));    // QW = W Q^T
     RUN(kron_gemm(c, L.W2, T.Mp, L.S2, T.Mp, L.SW, S.Mp, rows, S.Mp, T.Mp, TRI_FULL, nullptr, nullptr, st));   // SW = W^2 S2^T
     ProfScope ps(c, PC_POINT, st);
@@ -125,6 +144,12 @@ int kron_chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, i
     KFactor &S = L.f[0], &T = L.f[1];
     const int Msp = S.Mp, Mtp = T.Mp;
     const long long es = (long long)rows * Msp, et = (long long)rows * Mtp;
+    if (kron_mid_fused(c, L)) {
+        // Vs, Vt, P1, P2 in one launch: QtU = U Q and StU2 = U^2 S2 stay in registers
+        ProfScope ps(c, PC_GEMM, st);
+        CK(launch_kron_mid(true, kron_mid_args(L, theta, rows), c->n_sms, st));
+        c->launches++;
+    } else {
     {
         ProfScope ps(c, PC_KGRAD, st);
         kron_bwd_s_kernel<<<(unsigned)((es + 255) / 256), 256, 0, st>>>(S.Ub, L.QW, L.SW, S.Kb, Msp, L.gm, L.gv, T.p, es, S.Vb, L.P1, L.P2, L.U2);
@@ -136,6 +161,7 @@ int kron_chunk_backward(zigp_ctx* c, int l, const double* theta, long long n0, i
         ProfScope ps(c, PC_KGRAD, st);
         kron_bwd_t_kernel<<<(unsigned)((et + 255) / 256), 256, 0, st>>>(T.Ub, L.QtU, L.StU2, T.Kb, Mtp, L.gm, L.gv, S.p, et, T.Vb);
         LAUNCHED();
+    }
     }
     RUN(kron_nt(c, L.P1, Msp, Msp, T.Ub, Mtp, Mtp, L.Qbar_splits, L.nsplit, rows, st));      // Qbar  += (gm U)^T W
     RUN(kron_nt(c, L.P2, Msp, Msp, L.W2, Mtp, Mtp, L.S2bar_splits, L.nsplit, rows, st));     // S2bar += (gv U^2)^T W^2

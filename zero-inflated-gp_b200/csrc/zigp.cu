@@ -140,8 +140,9 @@ struct zigp_ctx {
     // gradient kernel ALU-bound), step 574.4 -> 590.5 ms.  Parity-green (72 tests with the switch on), NOT the default.
     bool oz_kplanes = false;
     // Kronecker variant: factors padded to 64 run their forward / backward product chains as one fused kernel each (kron_fused.cuh);
-    // ZIGP_KRON_FUSED=0: the unfused launches (any factor size)
-    bool kron_fused = true; int n_sms = 0;
+    // and, when both factors are, the Ms x Mt products between them with the moments / the V terms (level 2, default).
+    // ZIGP_KRON_FUSED=0: the unfused launches (any factor size), 1: factor chains only
+    int kron_fused = 2; int n_sms = 0;
     // gradient-sum kernel of the planes pipeline on large chunks: one balanced wave of CTAs (ZIGP_KG_BALANCED=0: 128-row blocks, 2.3 waves)
     bool kg_balanced = true;
     std::vector<cudaEvent_t> evpool; size_t evnext = 0;
@@ -1126,7 +1127,7 @@ int zigp_create_kron_ex(zigp_ctx** out, int device, int Ms_f, int Mt_f, int Ms_g
     c->chunk = rup(chunk, 512);
     const int Ms[2] = {Ms_f, Ms_g}, Mt[2] = {Mt_f, Mt_g};
     { int r = kron_alloc(c, Ms, Mt); if (r) return fail(r); }
-    if (const char* kf = getenv("ZIGP_KRON_FUSED")) c->kron_fused = atoi(kf) != 0;
+    if (const char* kf = getenv("ZIGP_KRON_FUSED")) c->kron_fused = atoi(kf);
     if (cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->n_sms < 1) { c->err = "cudaDeviceGetAttribute(multiProcessorCount) failed"; return fail(ZIGP_ECUDA); }
     if (const char* pz = getenv("ZIGP_POTRF")) c->potrf_panel = atoi(pz) != 0;
     if (cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM) != cudaSuccess ||
