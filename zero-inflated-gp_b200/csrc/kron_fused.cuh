@@ -9,7 +9,7 @@
 //   backward (per factor):  v (read)  ->  t = v T^T  ->  kv = t T (= K^-1 v)  ->  G = (kv - gv po u) * k  ->  S0, S1, Q2 column sums
 //                           replaces 2 x gemm_tn_f64 + kron_kgrad_kernel and the tmp / KV arrays (never written)
 //
-// Persistent CTAs (3 per SM, 4 warps, 64-row tiles): the 64 x 64 factor matrix T stays in shared memory for the whole launch, the products
+// Persistent CTAs (2 per SM, 8 warps, 64-row tiles): the 64 x 64 factor matrix T stays in shared memory for the whole launch, the products
 // run on the DMMA pipe with the fragment mapping and triangular skipping of gemm_tn_f64 (gemm_f64.cuh), the row tile is the only per-tile
 // traffic.  Same arithmetic per output element as the unfused launches (same k order), reference: scripts/onoff.py:186-213, 243-250.
 #pragma once
@@ -20,8 +20,14 @@ namespace zigp {
 constexpr int KF_M = 64;                 // factor width (padded inducing points)
 constexpr int KF_ROWS = 64;              // rows per tile
 constexpr int KF_STR = KF_M + 4;         // shared-memory row stride: == 4 (mod 16) doubles, conflict-free fragment loads
-constexpr int KF_THREADS = 128;
-constexpr int KF_CTAS = 3;               // resident CTAs per SM (70 KB of shared memory and <= 168 registers each)
+#ifndef ZIGP_KF_FM
+#define ZIGP_KF_FM 2
+#endif
+constexpr int KF_FM = ZIGP_KF_FM;        // 8-row fragments per warp: warp tile (8 KF_FM) x 32; 2 -> 8 warps per CTA, 4 -> 4 warps
+constexpr int KF_WM = KF_ROWS / (8 * KF_FM);             // warps along the rows (x 2 column halves)
+constexpr int KF_THREADS = 64 * KF_WM;
+constexpr int KF_RQ = KF_THREADS / 64;   // row groups of the one-column-per-thread passes
+constexpr int KF_CTAS = KF_FM == 2 ? 2 : 3;              // resident CTAs per SM (70 KB of shared memory each; 128 / 168 registers per thread)
 constexpr int KF_MAXD = 3;               // input dimensions of one factor handled by the fused kernels (space: 2, time: 1 in the reference)
 
 struct KronFusedArgs {
@@ -50,19 +56,19 @@ __device__ __forceinline__ void kf_load_matrix(double* s, const double* __restri
 // product W[c][k] = T^T[c][k] = T[k][c].  With the row stride == 4 (mod 16) doubles both fragment patterns (row = c0 + lane / 4, col = k + lane % 4
 // and its transpose) touch 16 distinct 8-byte banks per half-warp, so the transpose costs nothing and the 34 KB of a second copy buy a third CTA per SM.
 template <int TRI>
-__device__ __forceinline__ void kf_tri_product(const double* sIn, const double* sT, int wm, int wn, int fr, int fk, double (&acc)[4][4][2]) {
+__device__ __forceinline__ void kf_tri_product(const double* sIn, const double* sT, int wm, int wn, int fr, int fk, double (&acc)[KF_FM][4][2]) {
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < KF_FM; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    const double* cIn = sIn + (wm * 32 + fr) * KF_STR + fk;
+    const double* cIn = sIn + (wm * 8 * KF_FM + fr) * KF_STR + fk;
     const double* cW = (TRI == TRI_LOWER) ? sT + (wn * 32 + fr) * KF_STR + fk : sT + fk * KF_STR + wn * 32 + fr;
     constexpr int WJ = (TRI == TRI_LOWER) ? 8 * KF_STR : 8, WK = (TRI == TRI_LOWER) ? 1 : KF_STR;     // steps of the column fragment / of k
 #pragma unroll
     for (int kk = 0; kk < KF_M; kk += 4) {
-        double a[4];
+        double a[KF_FM];
 #pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = cIn[i * 8 * KF_STR + kk];
+        for (int i = 0; i < KF_FM; i++) a[i] = cIn[i * 8 * KF_STR + kk];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int jc = wn * 32 + 8 * j;
@@ -70,18 +76,18 @@ __device__ __forceinline__ void kf_tri_product(const double* sIn, const double* 
             if (needed) {
                 const double b = cW[j * WJ + kk * WK];
 #pragma unroll
-                for (int i = 0; i < 4; i++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
+                for (int i = 0; i < KF_FM; i++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
             }
         }
     }
 }
 
-__device__ __forceinline__ void kf_store_tile(double* sOut, int wm, int wn, int fr, int fk, const double (&acc)[4][4][2]) {
+__device__ __forceinline__ void kf_store_tile(double* sOut, int wm, int wn, int fr, int fk, const double (&acc)[KF_FM][4][2]) {
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < KF_FM; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            *reinterpret_cast<double2*>(sOut + (wm * 32 + i * 8 + fr) * KF_STR + wn * 32 + j * 8 + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2*>(sOut + (wm * 8 * KF_FM + i * 8 + fr) * KF_STR + wn * 32 + j * 8 + 2 * fk) = make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 // MODE 0: forward chain, MODE 1: backward chain.  DT = input dimensions of the factor (1 .. KF_MAXD).
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
     double* srow = sx + KF_ROWS * DT;                    // [KF_ROWS]: backward -gv po ; forward: |a|^2 of the second column half
     double* sred = srow + KF_ROWS;                       // backward: [2][1 + 2 DT][64] column sums of the two row halves ; forward: |a|^2, first half
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1, fr = lane >> 2, fk = lane & 3;
+    const int wm = warp % KF_WM, wn = warp / KF_WM, fr = lane >> 2, fk = lane & 3;
 
     kf_load_matrix(sT, p.T, tid);
     cp_async_commit();
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
             // kernel rows (kgen_kernel's arithmetic), written to K and kept in shared memory as the first product's operand
             const int m = tid & 63;
 #pragma unroll 4
-            for (int r = tid >> 6; r < KF_ROWS; r += 2) {
+            for (int r = tid >> 6; r < KF_ROWS; r += KF_RQ) {
                 double kv = 0.0;
                 if (row0 + r < p.nvalid && m < p.M) {
                     double r2 = 0.0;
@@ -149,13 +155,13 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
             __syncthreads();
         }
         // ---- first product: (k | v) T^T ---------------------------------------------------------------------------------------
-        double acc[4][4][2];
+        double acc[KF_FM][4][2];
         kf_tri_product<TRI_LOWER>(sIn, sT, wm, wn, fr, fk, acc);
         if (MODE == 0) {
             // a: to global, and its row statistics |a|^2 (column halves combined through shared memory)
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int r = wm * 32 + i * 8 + fr;
+            for (int i = 0; i < KF_FM; i++) {
+                const int r = wm * 8 * KF_FM + i * 8 + fr;
                 double ssq = 0.0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -175,8 +181,8 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
         kf_tri_product<TRI_UPPER>(sIn, sT, wm, wn, fr, fk, acc);
         if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const long long o = (long long)(row0 + wm * 32 + i * 8 + fr) * KF_M + wn * 32 + 2 * fk;
+            for (int i = 0; i < KF_FM; i++) {
+                const long long o = (long long)(row0 + wm * 8 * KF_FM + i * 8 + fr) * KF_M + wn * 32 + 2 * fk;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     *reinterpret_cast<double2*>(p.U + o + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
@@ -190,12 +196,13 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
             __syncthreads();                                           // every warp is done reading the t tile
             kf_store_tile(sIn, wm, wn, fr, fk, acc);
             __syncthreads();
+            constexpr int RPT = KF_ROWS / KF_RQ;                      // rows per thread
             const int m = tid & 63, rh = tid >> 6;
-            const double* gu = p.U + (long long)(row0 + rh * 32) * KF_M + m;
-            const double* gk = p.K + (long long)(row0 + rh * 32) * KF_M + m;
+            const double* gu = p.U + (long long)(row0 + rh * RPT) * KF_M + m;
+            const double* gk = p.K + (long long)(row0 + rh * RPT) * KF_M + m;
 #pragma unroll 8
-            for (int rr = 0; rr < 32; rr++) {
-                const int r = rh * 32 + rr;
+            for (int rr = 0; rr < RPT; rr++) {
+                const int r = rh * RPT + rr;
                 const double G = (sIn[r * KF_STR + m] + srow[r] * gu[(long long)rr * KF_M]) * gk[(long long)rr * KF_M];
                 s0 += G;
 #pragma unroll
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
     }
     cp_async_wait<0>();                                                // (a CTA without tiles still has the matrix loads in flight)
     if (MODE == 1) {
-        // thread = (column m, row half): the two halves meet in shared memory, then into this CTA's slot
+        // thread = (column m, row group): the groups meet in shared memory, then into this CTA's slot
         __syncthreads();
         const int m = tid & 63, rh = tid >> 6;
         sred[(rh * (1 + 2 * DT) + 0) * KF_M + m] = s0;
@@ -217,7 +224,12 @@ __global__ void __launch_bounds__(KF_THREADS, KF_CTAS) kron_chain_kernel(const K
         for (int d = 0; d < DT; d++) { sred[(rh * (1 + 2 * DT) + 1 + d) * KF_M + m] = s1[d]; sred[(rh * (1 + 2 * DT) + 1 + DT + d) * KF_M + m] = q2[d]; }
         __syncthreads();
         double* out = p.partial + (long long)blockIdx.x * (1 + 2 * DT) * KF_M;
-        for (int e = tid; e < (1 + 2 * DT) * KF_M; e += KF_THREADS) out[e] += sred[e] + sred[(1 + 2 * DT) * KF_M + e];
+        for (int e = tid; e < (1 + 2 * DT) * KF_M; e += KF_THREADS) {
+            double v = 0.0;
+#pragma unroll
+            for (int g = 0; g < KF_RQ; g++) v += sred[g * (1 + 2 * DT) * KF_M + e];
+            out[e] += v;
+        }
     }
 }
 
@@ -426,7 +438,7 @@ inline cudaError_t launch_kron_mid(bool backward, const KronMidArgs& a, int n_sm
 }
 
 constexpr size_t kf_smem_bytes(int dt) {
-    return (size_t)(2 * KF_M * KF_STR + KF_ROWS * dt + KF_ROWS + 2 * (1 + 2 * dt) * KF_M) * sizeof(double);
+    return (size_t)(2 * KF_M * KF_STR + KF_ROWS * dt + KF_ROWS + KF_RQ * (1 + 2 * dt) * KF_M) * sizeof(double);
 }
 
 // grid: persistent, at most KF_CTAS CTAs per SM (and, backward, at most max_slots CTAs: every CTA owns one slot of `partial`)
