@@ -449,7 +449,9 @@ def run_ours(a):
         achieved = gflop / (kern_ms * 1e-3) * 1e-12 if kern_ms else 0.0
     if kron:
         # per point and latent the contraction class runs 8 triangular factor products (Ms^2 or Mt^2 flop each) and 4 full
-        # Ms x Mt products (2 Ms Mt flop each); the rate is averaged over all of them
+        # Ms x Mt products (2 Ms Mt flop each); the rate is averaged over all of them.  With the fused kernels (csrc/kron_fused.cuh, 64-wide
+        # factors) the class time also contains what they absorbed: the kernel rows (one exp per element), the moments, the V terms and the
+        # kernel-gradient sums -- so `achieved` understates the DMMA rate of the products themselves
         gflop = 2.0 * (4.0 * (a.ms ** 2 + a.mt ** 2) + 8.0 * a.ms * a.mt) * n_loc
         achieved = gflop / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else 0.0
 
@@ -549,7 +551,10 @@ def roofline_head(int8, kron, achieved, dgemm_tf, M, m, i8pk=None):
                 "frac_of_burst_peak": (achieved * prods / i8pk["burst_tops"]) if i8pk else None,
                 "fp64_equivalent_tflops": achieved, "dgemm_tflops_measured": dgemm_tf,
                 "fp64_equivalent_over_dgemm": achieved / dgemm_tf if dgemm_tf else None}
-    return {"bound": "tensor", "kernel": "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)", "achieved": achieved, "peak": dgemm_tf,
+    kname = ("kron_chain_kernel<fwd|bwd> + kron_mid_fwd/bwd_kernel (DMMA.8x8x4; per 64-row tile two chained 64x64 products with the intermediate in shared "
+             "memory, fused with the kernel rows / moments / gradient sums; factors padded to 64 -- other sizes run gemm_tn_f64 per product)") if kron else \
+        "gemm_tn_f64<64,64,32,32,2,3> (DMMA.8x8x4; 64x64 tiles, k-slab 32, 3 CTAs per SM)"
+    return {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": dgemm_tf,
             "unit": "TFLOP/s", "frac": achieved / dgemm_tf if dgemm_tf else None, "traffic": traffic_per_launch(M, ctx_chunk_rows(m)) if not kron else None,
             "peak_source": "cuBLAS DGEMM 4096^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue ceiling 37.1 TFLOP/s, profiles/microbench)"}
 

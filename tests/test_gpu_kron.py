@@ -224,6 +224,38 @@ def test_kron_comparison_models_against_oracle(model):
     assert abs(float(m.build_prior_kl()) - kl) <= 1e-10 * abs(kl)
 
 
+def test_kron_fused_kernels_equal_the_unfused_launches(monkeypatch):
+    """csrc/kron_fused.cuh against the launch-per-product pipeline it replaces for 64-wide factors, on BASELINE configs[4]'s own 64 x 64 grid:
+    ZIGP_KRON_FUSED=2 (default: factor chains k -> a -> u and v -> K^-1 v -> gradient sums, plus the Ms x Mt products fused with the moments /
+    the V terms), =1 (factor chains only), =0 (unfused).  Same arithmetic per element in the products (same k order), so the ELBO agrees to
+    1e-13 and the packed gradient to 1e-12 of its norm (only the order of the per-column / per-row sums differs); ragged three-chunk problem
+    (the last chunk is mostly padding rows), and the 9-tuple of the prediction path, which runs the fused forward kernels alone."""
+    N, Ms, Mt = 70_001, 64, 64
+    X, Y = synth.make_data(N, 3, seed=31)
+    p = synth.make_kron_params(Ms, Mt, 2, 1, seed=31)
+    rng = np.random.default_rng(31)
+    for lat in "fg":
+        p["u_%sm" % lat] = 0.3 * rng.standard_normal((Ms * Mt, 1)); p["u_%ss_sqrt" % lat] = 0.5 + rng.random((Ms * Mt, 1))
+    outs, preds = {}, {}
+    for level in ("0", "1", "2"):
+        monkeypatch.setenv("ZIGP_KRON_FUSED", level)
+        m = build(X, Y, p, chunk_rows=32768)
+        m.build_likelihood()
+        outs[level] = m._last_out.cpu().numpy().copy()
+        preds[level] = np.concatenate(m.predict_onoff(X[:1000])["all"], 1)
+        del m
+        torch.cuda.empty_cache()
+    ref = outs["0"]
+    assert ref[3] == 0 and np.all(np.isfinite(ref))
+    for level in ("1", "2"):
+        o = outs[level]
+        assert o[3] == 0
+        for i in range(3):
+            assert abs(o[i] - ref[i]) <= 1e-13 * abs(ref[i]), (level, i, o[i], ref[i])
+        assert np.linalg.norm(o[4:] - ref[4:]) <= 1e-12 * np.linalg.norm(ref[4:]), (level, np.linalg.norm(o[4:] - ref[4:]) / np.linalg.norm(ref[4:]))
+        assert np.allclose(preds[level], preds["0"], rtol=1e-12, atol=1e-13)
+
+
 def test_kron_full_grid_properties_at_scale():
     """BASELINE.json configs[4]'s inducing grid (64 x 64, M = 4096) at N = 2^23 points per evaluation, far beyond the oracle: the data term
     is additive over the halves of the data, ELBO and packed gradient do not depend on the row order, repeated evaluations are bit-identical"""
