@@ -445,7 +445,7 @@ constexpr size_t kf_smem_bytes(int dt) {
 template <int MODE>
 inline cudaError_t launch_kron_chain(const KronFusedArgs& a, int n_sms, int max_slots, cudaStream_t st) {
     const int ntiles = a.rows / KF_ROWS;
-    static int ctas = 0;                                               // ZIGP_KF_CTAS=2: two CTAs per SM (A/B switch; the kernels fit three)
+    static int ctas = 0;                                               // ZIGP_KF_CTAS=1: one CTA per SM (A/B switch; default KF_CTAS)
     if (!ctas) { const char* e = getenv("ZIGP_KF_CTAS"); ctas = (e && atoi(e) >= 1 && atoi(e) <= KF_CTAS) ? atoi(e) : KF_CTAS; }
     int grid = std::min(ntiles, ctas * n_sms);
     if (MODE == 1) grid = std::min(grid, max_slots);

@@ -218,7 +218,7 @@ int kron_accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
         for (int l = 0; l < c->nlat; l++) RUN(kron_chunk_backward(c, l, theta, n0, nvalid, rows, st));
     }
     ProfScope psr(c, PC_REDUCE, st);
-    reduce_slots_kernel<<<1, 32, 0, st>>>(c->pt_partial, 4, c->pt_slots, c->accum, 4);
+    reduce_slots_tall_kernel<4><<<1, 256, 0, st>>>(c->pt_partial, 4, c->pt_slots, c->accum, 4);
     LAUNCHED();
     for (int l = 0; l < c->nlat; l++) {
         KLatent& L = c->klat[l];
@@ -232,7 +232,9 @@ int kron_accumulate(zigp_ctx* c, const double* theta, cudaStream_t st) {
             const long long MM = (long long)F.Mp * F.Mp, VL = (long long)(1 + 2 * F.D) * F.Mp;
             reduce_slots_kernel<<<(unsigned)((MM + 255) / 256), 256, 0, st>>>(F.F_splits, MM, L.nsplit, F.accFT, MM);
             LAUNCHED();
-            reduce_slots_kernel<<<(unsigned)((VL + 255) / 256), 256, 0, st>>>(F.kg_partial, VL, c->kg_slots, F.accV, VL);
+            // the fused backward chain owns one slot per persistent CTA: only those were written (the rest of the zeroed buffer is not read)
+            const int used = kron_factor_fused(c, F) ? std::min(c->kg_slots, KF_CTAS * c->n_sms) : c->kg_slots;
+            reduce_slots_kernel<<<(unsigned)((VL + 255) / 256), 256, 0, st>>>(F.kg_partial, VL, used, F.accV, VL);
             LAUNCHED();
         }
     }

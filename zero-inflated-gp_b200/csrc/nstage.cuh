@@ -303,6 +303,27 @@ __global__ void reduce_slots_kernel(const double* __restrict__ src, long long st
     dst[i] = s;
 }
 
+// the same for FEW outputs and MANY slots (the likelihood partials of a 2M-row Kronecker chunk: 4 outputs x 8192 slots took 335 us with one
+// thread per output): OPB outputs per block, 256 / OPB threads per output stride over the slots, partials combined in a fixed order
+template <int OPB>
+__global__ void __launch_bounds__(256) reduce_slots_tall_kernel(const double* __restrict__ src, long long stride, int nslots, double* __restrict__ dst, long long len) {
+    constexpr int SG = 256 / OPB;
+    __shared__ double sh[SG][OPB];
+    const int ox = threadIdx.x % OPB, sg = threadIdx.x / OPB;
+    const long long i = (long long)blockIdx.x * OPB + ox;
+    double s = 0.0;
+    if (i < len)
+        for (int k = sg; k < nslots; k += SG) s += src[(long long)k * stride + i];
+    sh[sg][ox] = s;
+    __syncthreads();
+    if (sg == 0 && i < len) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int g = 0; g < SG; g++) t += sh[g][ox];
+        dst[i] = t;
+    }
+}
+
 // predict epilogue of the single-latent comparison models: lik 1 -> rows (fmean, fvar); lik 2 -> rows (p, p - p^2, fmean, fvar)
 // (scripts/svgp.py:123-133, scripts/classifier.py:128-142); the remaining rows of the 9 x n block are zero
 __global__ void predict1_kernel(const double* __restrict__ mf, const double* __restrict__ vf, int nvalid, long long n0, long long ntot, int lik,
