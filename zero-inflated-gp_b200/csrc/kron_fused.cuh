@@ -406,14 +406,23 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kron_mid_bwd_kernel(const KronM
             }
         }
         // space side, one column per thread over 16 rows: coalesced rows of QW, SW, Ks in, Vs, P1, P2 out; u from the tile in shared memory
+        // (all 24 loads of a batch of 8 rows are issued before the first use: with the loads consumed one row at a time this pass held 57 % of
+        // the kernel's stall samples, profiles/ncu_kron_fused_r02.txt)
         const int m = tid & 63, rq = tid >> 6;
-#pragma unroll 4
-        for (int rr = 0; rr < 16; rr++) {
-            const int r = rq * 16 + rr;
-            const long long e = (long long)(row0 + r) * KF_M + m;
-            const double u = sIn[r * KF_STR + m], g1 = sgm[r], g2 = sgv[r];
-            p.Vs[e] = g1 * p.QW[e] + 2.0 * g2 * u * p.SW[e] - g2 * spt[r] * p.Ks[e];
-            p.P1[e] = g1 * u; p.P2[e] = g2 * u * u;
+#pragma unroll
+        for (int hb = 0; hb < 2; hb++) {
+            const long long e0 = (long long)(row0 + rq * 16 + hb * 8) * KF_M + m;
+            double qw[8], sw[8], ks[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) { qw[rr] = p.QW[e0 + rr * KF_M]; sw[rr] = p.SW[e0 + rr * KF_M]; ks[rr] = p.Ks[e0 + rr * KF_M]; }
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const int r = rq * 16 + hb * 8 + rr;
+                const long long e = e0 + rr * KF_M;
+                const double u = sIn[r * KF_STR + m], g1 = sgm[r], g2 = sgv[r];
+                p.Vs[e] = g1 * qw[rr] + 2.0 * g2 * u * sw[rr] - g2 * spt[r] * ks[rr];
+                p.P1[e] = g1 * u; p.P2[e] = g2 * u * u;
+            }
         }
     }
     cp_async_wait<0>();
